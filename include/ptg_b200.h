@@ -1,0 +1,133 @@
+/*
+ * ptg_b200.h -- C ABI of the B200-native particle-to-grid deposition library
+ *               (libptg_b200.so, sm_100a only).
+ *
+ * This is the drop-in boundary for postpic's one native component,
+ *     postpic/particles/_particlestogrid.pyx
+ *         histogram    :38-130     (1-D deposit)
+ *         histogram2d  :135-278    (2-D deposit)
+ *         histogram3d  :284-465    (3-D deposit)
+ * and for the two full-array passes its only caller makes before it,
+ *     postpic/particles/_routines.py:115-127   (np.min / np.max when a range end is None)
+ * and the one pass the caller's caller makes after it,
+ *     postpic/particles/particles.py:1101-1102  (h /= dV).
+ *
+ * Conventions
+ *   - plain C types, no CUDA/torch types in any signature; `stream` is a cudaStream_t
+ *     passed as void* (NULL = the legacy default stream);
+ *   - every function returns PTG_OK (0) or a negative PTG_E* code, never throws, never
+ *     prints; ptg_last_error() returns a thread-local human readable message;
+ *   - "device" pointers are CUDA device pointers on the current device, "host"
+ *     pointers are ordinary process memory (pageable or pinned);
+ *   - element strides: strides[k] is the distance, in doubles, between consecutive
+ *     particles of array k (k = 0,1,2 for x,y,z and 3 for the weights); NULL means
+ *     all arrays are contiguous (stride 1).  The reference accepts arbitrarily strided
+ *     1-D buffers (np.ndarray[np.double_t, ndim=1] without mode='c', pyx:38,135,284);
+ *   - the grid is the reference's ghost-padded accumulator (pyx:81,96,114,193,219,249,
+ *     354,387,426): C order, dims[a] = bins[a] + 2*shape, float64.  The histogram the
+ *     reference returns is the interior view grid[shape:shape+bins[a], ...].
+ *   - lo[a] and inv[a] are computed by the caller exactly as the reference does
+ *     (pyx:53-60: degenerate-range widening, inv = 1.0/(hi-lo)*bins) -- or by
+ *     ptg_axis_setup() below, which restates that arithmetic in C.
+ *
+ * There is NO CPU fallback: on a machine without an sm_100-class GPU every compute
+ * entry point returns PTG_ENODEVICE.
+ */
+#ifndef PTG_B200_H
+#define PTG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTG_ABI_VERSION 1
+
+/* ---- return codes ------------------------------------------------------------- */
+#define PTG_OK            0
+#define PTG_EINVAL       -1   /* bad argument (ndim, shape, bins, NULL pointer, n < 0 ...)        */
+#define PTG_ECUDA        -2   /* a CUDA runtime call or kernel failed; see ptg_last_error()       */
+#define PTG_ENOMEM       -3   /* workspace too small / allocation failed                          */
+#define PTG_ENODEVICE    -4   /* no usable sm_100 GPU                                             */
+#define PTG_EUNSUPPORTED -5   /* valid request this build cannot serve (e.g. grid > 2^31 cells)   */
+
+/* ---- flags for the deposit entry points ------------------------------------------ */
+#define PTG_ZERO_GRID        0x1u   /* clear the padded grid before depositing                     */
+/* deposition method (bits 4..7); AUTO picks by grid size / dimensionality                       */
+#define PTG_METHOD_MASK      0xF0u
+#define PTG_METHOD_AUTO      0x00u
+#define PTG_METHOD_GLOBAL    0x10u  /* one RED.E.ADD.F64 per stencil cell, straight to L2          */
+#define PTG_METHOD_ROWS      0x20u  /* lanes regrouped so one RED instruction covers whole stencil
+                                       rows (sector-coalesced L2 reductions)                      */
+#define PTG_METHOD_TILED     0x30u  /* shared-memory privatised sub-grid tile per CTA, warp-
+                                       aggregated updates, tile merge to HBM                      */
+#define PTG_METHOD_SORTED    0x40u  /* deterministic: sort by cell + segmented reduce, no atomics  */
+
+/* ---- introspection ------------------------------------------------------------- */
+int         ptg_abi_version(void);
+const char *ptg_last_error(void);
+const char *ptg_strerror(int code);
+/* fills name (<= name_len bytes), SM count, L2 bytes, total HBM bytes of `device`. */
+int ptg_device_info(int device, char *name, int name_len, int *sm_count,
+                    int64_t *l2_bytes, int64_t *hbm_bytes, int *cc_major, int *cc_minor);
+
+/* ---- host-side axis set-up (pyx:53-60, :155-169, :307-328) ----------------------- */
+/* in: range ends and bin count.  out: widened lo/hi, inv = 1.0/(hi-lo)*bins. */
+int ptg_axis_setup(double lo_in, double hi_in, int bins, double *lo, double *hi, double *inv);
+
+/* ---- device-resident deposit (replaces the loops pyx:70-129, :181-276, :341-463) -- */
+/*
+ * x,y,z,w: device pointers (y,z ignored beyond ndim; w NULL = the reference's
+ * `weights is None` branch).  grid: device pointer to the padded accumulator.
+ * The call is asynchronous on `stream`.  workspace may be NULL when
+ * ptg_workspace_bytes() returns 0 for the same arguments.
+ */
+int ptg_deposit_f64(int ndim, int shape, int64_t n,
+                    const double *x, const double *y, const double *z, const double *w,
+                    const int64_t *strides,
+                    const double *lo, const double *inv, const int *bins,
+                    double *grid, unsigned flags,
+                    void *workspace, size_t workspace_bytes, void *stream);
+
+size_t ptg_workspace_bytes(int ndim, int shape, int64_t n, const int *bins, unsigned flags);
+
+/* number of padded cells = prod(bins[a] + 2*shape); 0 on bad arguments */
+int64_t ptg_padded_cells(int ndim, int shape, const int *bins);
+
+/* ---- helpers on device buffers ------------------------------------------------------ */
+/* out2[0] = min, out2[1] = max over x[0..n) (device pointer out2; NaNs are ignored like
+ * they are not by np.min -- see INTEGRATION.md); replaces _routines.py:117-126.        */
+int ptg_minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, void *stream);
+/* grid[i] *= factor for i in [0,count): the h /= dV of particles.py:1101-1102 with
+ * factor = 1/dV computed by the caller.                                               */
+int ptg_scale_f64(double *grid, int64_t count, double factor, void *stream);
+int ptg_zero_f64(double *grid, int64_t count, void *stream);
+
+/* ---- host-buffer drop-in: H2D + deposit + D2H in one call --------------------------- */
+/*
+ * Same meaning as ptg_deposit_f64 but x,y,z,w and grid are HOST pointers.  Particles
+ * are streamed to the GPU in chunks through a small ring of device buffers so that the
+ * PCIe copy of chunk k+1 overlaps the deposit of chunk k; the padded grid is copied
+ * back to `grid` (which is overwritten, not accumulated into) before the call returns.
+ * Synchronous.  `device` < 0 means the current device.
+ */
+int ptg_histogram_host_f64(int ndim, int shape, int64_t n,
+                           const double *x, const double *y, const double *z, const double *w,
+                           const int64_t *strides,
+                           const double *lo, const double *inv, const int *bins,
+                           double *grid, unsigned flags, int device);
+int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2, int device);
+/* release the cached per-device staging buffers and streams of the host entry points */
+int ptg_release(void);
+
+/* ---- test hooks (used by tests/ only) ------------------------------------------------- */
+/* out[i] = the library's division-by-6 of in[i] (device pointers) -- checked bit-for-bit
+ * against IEEE division by the tests.                                                   */
+int ptg_selftest_div6(int64_t n, const double *in, double *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTG_B200_H */

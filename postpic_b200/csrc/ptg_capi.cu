@@ -1,0 +1,426 @@
+// ptg_capi.cu -- the extern "C" boundary declared in include/ptg_b200.h.
+//
+// Argument validation, method selection, per-device cached state (SM count, streams,
+// staging ring for the host-buffer entry points) and the H2D -> deposit -> D2H
+// pipeline.  No CUDA or C++ type crosses the boundary; nothing here throws.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/ptg_b200.h"
+#include "ptg_internal.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define PTG_CUDA(call)                                                                  \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return fail(e__ == cudaErrorMemoryAllocation ? PTG_ENOMEM : PTG_ECUDA,      \
+                        "%s failed: %s", #call, cudaGetErrorString(e__));               \
+    } while (0)
+
+constexpr int kMaxDevices = 16;
+constexpr int kSlots = 3;                         // staging ring depth
+constexpr int64_t kChunk = int64_t(1) << 22;      // particles per pipeline chunk (32 MiB per array)
+
+struct DeviceState {
+    bool probed = false;
+    bool usable = false;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    // host-entry staging
+    cudaStream_t stream[kSlots] = {};
+    double *slot[kSlots] = {};                    // each 4 * kChunk doubles
+    double *grid = nullptr;
+    int64_t grid_cells = 0;
+    double *scratch2 = nullptr;                   // 2 doubles for min/max
+    bool staged = false;
+};
+
+DeviceState g_dev[kMaxDevices];
+std::mutex g_mu;
+
+int probe(int device, DeviceState **out) {
+    if (device < 0) {
+        cudaError_t e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return fail(PTG_ENODEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    }
+    if (device >= kMaxDevices) return fail(PTG_EINVAL, "device index %d too large", device);
+    DeviceState &d = g_dev[device];
+    if (!d.probed) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!d.probed) {
+            cudaDeviceProp p;
+            cudaError_t e = cudaGetDeviceProperties(&p, device);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                return fail(PTG_ENODEVICE, "no usable CUDA device %d: %s", device, cudaGetErrorString(e));
+            }
+            d.sm_count = p.multiProcessorCount;
+            d.cc_major = p.major;
+            d.cc_minor = p.minor;
+            d.usable = (p.major == 10);           // the library holds sm_100a code only
+            d.probed = true;
+        }
+    }
+    if (!d.usable)
+        return fail(PTG_ENODEVICE, "device %d is sm_%d%d; libptg_b200 contains sm_100a code only", device,
+                    d.cc_major, d.cc_minor);
+    *out = &d;
+    return PTG_OK;
+}
+
+int current_device_state(DeviceState **out) { return probe(-1, out); }
+
+int validate(int ndim, int shape, int64_t n, const double *x, const double *y, const double *z,
+             const double *lo, const double *inv, const int *bins, const double *grid) {
+    if (ndim < 1 || ndim > 3) return fail(PTG_EINVAL, "ndim must be 1, 2 or 3 (got %d)", ndim);
+    if (shape < 0 || shape > 3) return fail(PTG_EINVAL, "unknown particle shape %d", shape);
+    if (n < 0) return fail(PTG_EINVAL, "negative particle count");
+    if (!lo || !inv || !bins || !grid) return fail(PTG_EINVAL, "lo/inv/bins/grid must not be NULL");
+    if (n > 0 && (!x || (ndim >= 2 && !y) || (ndim >= 3 && !z)))
+        return fail(PTG_EINVAL, "coordinate pointer is NULL");
+    for (int a = 0; a < ndim; ++a)
+        if (bins[a] < 1) return fail(PTG_EINVAL, "bins[%d] = %d must be >= 1", a, bins[a]);
+    const int64_t cells = ptg_padded_cells(ndim, shape, bins);
+    if (cells <= 0 || cells >= (int64_t(1) << 31))
+        return fail(PTG_EUNSUPPORTED, "padded grid has %lld cells; supported: < 2^31", (long long)cells);
+    return PTG_OK;
+}
+
+void fill_params(ptg::DepositParams &P, int ndim, int shape, int64_t n, const double *x, const double *y,
+                 const double *z, const double *w, const int64_t *strides, const double *lo,
+                 const double *inv, const int *bins, double *grid) {
+    memset(&P, 0, sizeof P);
+    P.p[0] = x; P.p[1] = y; P.p[2] = z; P.p[3] = w;
+    for (int k = 0; k < 4; ++k) P.stride[k] = strides ? strides[k] : 1;
+    P.n = n;
+    for (int a = 0; a < 3; ++a) {
+        const bool on = a < ndim;
+        P.lo[a] = on ? lo[a] : 0.0;
+        P.inv[a] = on ? inv[a] : 1.0;
+        P.bins[a] = on ? bins[a] : 1;
+        P.fbins[a] = (double)P.bins[a];
+        P.fbins_p1[a] = (double)P.bins[a] + 1.0;
+        P.dims[a] = on ? bins[a] + 2 * shape : 1;
+    }
+    P.grid = grid;
+}
+
+int pick_method(unsigned flags, int ndim, int shape) {
+    (void)ndim;
+    unsigned m = flags & PTG_METHOD_MASK;
+    if (m == PTG_METHOD_AUTO) m = shape == 0 ? PTG_METHOD_GLOBAL : PTG_METHOD_ROWS;
+    return (int)m;
+}
+
+int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double *x, const double *y,
+                   const double *z, const double *w, const int64_t *strides, const double *lo,
+                   const double *inv, const int *bins, double *grid, unsigned flags, cudaStream_t st) {
+    ptg::DepositParams P;
+    fill_params(P, ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid);
+    if (flags & PTG_ZERO_GRID)
+        PTG_CUDA(cudaMemsetAsync(grid, 0, (size_t)ptg_padded_cells(ndim, shape, bins) * sizeof(double), st));
+    const int method = pick_method(flags, ndim, shape);
+    switch (method) {
+        case PTG_METHOD_GLOBAL:
+            PTG_CUDA(ptg::deposit_global(ndim, shape, P, false, d->sm_count, st));
+            break;
+        case PTG_METHOD_ROWS:
+            PTG_CUDA(ptg::deposit_global(ndim, shape, P, shape > 0, d->sm_count, st));
+            break;
+        default:
+            return fail(PTG_EUNSUPPORTED, "deposition method 0x%x is not available in this build", method);
+    }
+    return PTG_OK;
+}
+
+int ensure_staging(DeviceState *d, int64_t cells) {
+    if (!d->staged) {
+        for (int k = 0; k < kSlots; ++k) {
+            PTG_CUDA(cudaStreamCreateWithFlags(&d->stream[k], cudaStreamNonBlocking));
+            PTG_CUDA(cudaMalloc(&d->slot[k], (size_t)4 * kChunk * sizeof(double)));
+        }
+        PTG_CUDA(cudaMalloc(&d->scratch2, 2 * sizeof(double)));
+        d->staged = true;
+    }
+    if (cells > d->grid_cells) {
+        if (d->grid) PTG_CUDA(cudaFree(d->grid));
+        d->grid = nullptr;
+        d->grid_cells = 0;
+        PTG_CUDA(cudaMalloc(&d->grid, (size_t)cells * sizeof(double)));
+        d->grid_cells = cells;
+    }
+    return PTG_OK;
+}
+
+// host -> device copy of m elements with an element stride on the host side
+cudaError_t h2d_strided(double *dst, const double *src, int64_t stride, int64_t m, cudaStream_t st) {
+    if (stride == 1) return cudaMemcpyAsync(dst, src, (size_t)m * 8, cudaMemcpyHostToDevice, st);
+    return cudaMemcpy2DAsync(dst, 8, src, (size_t)stride * 8, 8, (size_t)m, cudaMemcpyHostToDevice, st);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool active = false;
+    int enter(int device) {
+        if (device < 0) return PTG_OK;
+        if (cudaGetDevice(&prev) != cudaSuccess) return fail(PTG_ENODEVICE, "no CUDA device");
+        if (prev != device) {
+            if (cudaSetDevice(device) != cudaSuccess) return fail(PTG_ENODEVICE, "cannot select device %d", device);
+            active = true;
+        }
+        return PTG_OK;
+    }
+    ~DeviceGuard() { if (active) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ptg_abi_version(void) { return PTG_ABI_VERSION; }
+
+const char *ptg_last_error(void) { return g_err; }
+
+const char *ptg_strerror(int code) {
+    switch (code) {
+        case PTG_OK: return "ok";
+        case PTG_EINVAL: return "invalid argument";
+        case PTG_ECUDA: return "CUDA error";
+        case PTG_ENOMEM: return "out of memory / workspace too small";
+        case PTG_ENODEVICE: return "no usable sm_100 GPU";
+        case PTG_EUNSUPPORTED: return "unsupported request";
+        default: return "unknown error code";
+    }
+}
+
+int ptg_device_info(int device, char *name, int name_len, int *sm_count, int64_t *l2_bytes,
+                    int64_t *hbm_bytes, int *cc_major, int *cc_minor) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        (void)cudaGetLastError();
+        return fail(PTG_ENODEVICE, "no CUDA device present");
+    }
+    if (device < 0) cudaGetDevice(&device);
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, device);
+    if (e != cudaSuccess) return fail(PTG_ENODEVICE, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (name && name_len > 0) { strncpy(name, p.name, name_len - 1); name[name_len - 1] = 0; }
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = p.l2CacheSize;
+    if (hbm_bytes) *hbm_bytes = (int64_t)p.totalGlobalMem;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return PTG_OK;
+}
+
+int ptg_axis_setup(double lo_in, double hi_in, int bins, double *lo, double *hi, double *inv) {
+    if (!lo || !hi || !inv || bins < 1) return fail(PTG_EINVAL, "ptg_axis_setup: bad arguments");
+    double a = lo_in, b = hi_in;
+    // np.spacing(b): distance to the next representable number away from zero (pyx:54)
+    const double s = std::isfinite(b) ? std::nextafter(b, b < 0 ? -INFINITY : INFINITY) - b : NAN;
+    if (std::fabs(b - a) < s) { b += s; a -= s; }         // pyx:55-57
+    *lo = a;
+    *hi = b;
+    *inv = 1.0 / (b - a) * bins;                           // pyx:60, evaluated left to right
+    return PTG_OK;
+}
+
+int64_t ptg_padded_cells(int ndim, int shape, const int *bins) {
+    if (ndim < 1 || ndim > 3 || shape < 0 || shape > 3 || !bins) return 0;
+    int64_t c = 1;
+    for (int a = 0; a < ndim; ++a) {
+        if (bins[a] < 1) return 0;
+        const int64_t dim = (int64_t)bins[a] + 2 * shape;
+        if (c > (int64_t(1) << 40) / dim) return int64_t(1) << 41;   // saturate, caller rejects
+        c *= dim;
+    }
+    return c;
+}
+
+size_t ptg_workspace_bytes(int ndim, int shape, int64_t n, const int *bins, unsigned flags) {
+    (void)ndim; (void)shape; (void)n; (void)bins; (void)flags;
+    return 0;
+}
+
+int ptg_deposit_f64(int ndim, int shape, int64_t n, const double *x, const double *y, const double *z,
+                    const double *w, const int64_t *strides, const double *lo, const double *inv,
+                    const int *bins, double *grid, unsigned flags, void *workspace, size_t workspace_bytes,
+                    void *stream) {
+    (void)workspace; (void)workspace_bytes;
+    int rc = validate(ndim, shape, n, x, y, z, lo, inv, bins, grid);
+    if (rc) return rc;
+    DeviceState *d;
+    if ((rc = current_device_state(&d))) return rc;
+    return deposit_device(d, ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid, flags,
+                          (cudaStream_t)stream);
+}
+
+int ptg_minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, void *stream) {
+    if (n < 0 || !out2 || (n > 0 && !x)) return fail(PTG_EINVAL, "ptg_minmax_f64: bad arguments");
+    DeviceState *d;
+    int rc = current_device_state(&d);
+    if (rc) return rc;
+    PTG_CUDA(ptg::minmax_f64(n, x, stride, out2, d->sm_count, (cudaStream_t)stream));
+    return PTG_OK;
+}
+
+int ptg_scale_f64(double *grid, int64_t count, double factor, void *stream) {
+    if (!grid || count < 0) return fail(PTG_EINVAL, "ptg_scale_f64: bad arguments");
+    DeviceState *d;
+    int rc = current_device_state(&d);
+    if (rc) return rc;
+    PTG_CUDA(ptg::scale_f64(grid, count, factor, d->sm_count, (cudaStream_t)stream));
+    return PTG_OK;
+}
+
+int ptg_zero_f64(double *grid, int64_t count, void *stream) {
+    if (!grid || count < 0) return fail(PTG_EINVAL, "ptg_zero_f64: bad arguments");
+    DeviceState *d;
+    int rc = current_device_state(&d);
+    if (rc) return rc;
+    PTG_CUDA(cudaMemsetAsync(grid, 0, (size_t)count * sizeof(double), (cudaStream_t)stream));
+    return PTG_OK;
+}
+
+int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, const double *y,
+                           const double *z, const double *w, const int64_t *strides, const double *lo,
+                           const double *inv, const int *bins, double *grid, unsigned flags, int device) {
+    int rc = validate(ndim, shape, n, x, y, z, lo, inv, bins, grid);
+    if (rc) return rc;
+    if (strides)
+        for (int k = 0; k < 4; ++k)
+            if (strides[k] < 1) return fail(PTG_EINVAL, "host strides must be >= 1 (got %lld)", (long long)strides[k]);
+    DeviceGuard guard;
+    if ((rc = guard.enter(device))) return rc;
+    DeviceState *d;
+    if ((rc = current_device_state(&d))) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int64_t cells = ptg_padded_cells(ndim, shape, bins);
+    if ((rc = ensure_staging(d, cells))) return rc;
+
+    PTG_CUDA(cudaMemsetAsync(d->grid, 0, (size_t)cells * sizeof(double), d->stream[0]));
+    cudaEvent_t zeroed;
+    PTG_CUDA(cudaEventCreateWithFlags(&zeroed, cudaEventDisableTiming));
+    PTG_CUDA(cudaEventRecord(zeroed, d->stream[0]));
+    for (int k = 1; k < kSlots; ++k) PTG_CUDA(cudaStreamWaitEvent(d->stream[k], zeroed, 0));
+
+    const double *src[4] = {x, ndim >= 2 ? y : nullptr, ndim >= 3 ? z : nullptr, w};
+    const unsigned dflags = flags & ~PTG_ZERO_GRID;
+    int slot = 0;
+    for (int64_t off = 0; off < n; off += kChunk, slot = (slot + 1) % kSlots) {
+        const int64_t m = n - off < kChunk ? n - off : kChunk;
+        cudaStream_t st = d->stream[slot];
+        double *dptr[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int k = 0; k < 4; ++k) {
+            if (!src[k]) continue;
+            const int64_t s = strides ? strides[k] : 1;
+            dptr[k] = d->slot[slot] + k * kChunk;
+            PTG_CUDA(h2d_strided(dptr[k], src[k] + off * s, s, m, st));
+        }
+        rc = deposit_device(d, ndim, shape, m, dptr[0], dptr[1], dptr[2], dptr[3], nullptr, lo, inv, bins,
+                            d->grid, dflags, st);
+        if (rc) { cudaEventDestroy(zeroed); return rc; }
+    }
+    // join the ring on stream 0, then bring the padded grid home
+    for (int k = 1; k < kSlots; ++k) {
+        cudaEvent_t done;
+        PTG_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        PTG_CUDA(cudaEventRecord(done, d->stream[k]));
+        PTG_CUDA(cudaStreamWaitEvent(d->stream[0], done, 0));
+        PTG_CUDA(cudaEventDestroy(done));
+    }
+    PTG_CUDA(cudaMemcpyAsync(grid, d->grid, (size_t)cells * sizeof(double), cudaMemcpyDeviceToHost, d->stream[0]));
+    PTG_CUDA(cudaStreamSynchronize(d->stream[0]));
+    PTG_CUDA(cudaEventDestroy(zeroed));
+    return PTG_OK;
+}
+
+int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2, int device) {
+    if (n < 0 || !out2 || (n > 0 && !x) || stride < 1) return fail(PTG_EINVAL, "ptg_minmax_host_f64: bad arguments");
+    DeviceGuard guard;
+    int rc = guard.enter(device);
+    if (rc) return rc;
+    DeviceState *d;
+    if ((rc = current_device_state(&d))) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if ((rc = ensure_staging(d, 1))) return rc;
+    // chunked: reduce each chunk on the device, combine the (few) partial results on the host
+    double lo = INFINITY, hi = -INFINITY;
+    bool nan = false;
+    int slot = 0;
+    double part[kSlots][2] = {};
+    int64_t pending[kSlots];
+    for (int k = 0; k < kSlots; ++k) pending[k] = 0;
+    auto drain = [&](int k) -> int {
+        if (!pending[k]) return PTG_OK;
+        PTG_CUDA(cudaStreamSynchronize(d->stream[k]));
+        if (part[k][0] != part[k][0] || part[k][1] != part[k][1]) nan = true;
+        lo = part[k][0] < lo ? part[k][0] : lo;
+        hi = part[k][1] > hi ? part[k][1] : hi;
+        pending[k] = 0;
+        return PTG_OK;
+    };
+    for (int64_t off = 0; off < n; off += kChunk, slot = (slot + 1) % kSlots) {
+        if ((rc = drain(slot))) return rc;
+        const int64_t m = n - off < kChunk ? n - off : kChunk;
+        cudaStream_t st = d->stream[slot];
+        PTG_CUDA(h2d_strided(d->slot[slot], x + off * stride, stride, m, st));
+        double *res = d->slot[slot] + kChunk;      // second quarter of the slot is free here
+        PTG_CUDA(ptg::minmax_f64(m, d->slot[slot], 1, res, d->sm_count, st));
+        PTG_CUDA(cudaMemcpyAsync(part[slot], res, 16, cudaMemcpyDeviceToHost, st));
+        pending[slot] = m;
+    }
+    for (int k = 0; k < kSlots; ++k)
+        if ((rc = drain(k))) return rc;
+    out2[0] = nan ? NAN : lo;
+    out2[1] = nan ? NAN : hi;
+    return PTG_OK;
+}
+
+int ptg_release(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); return PTG_OK; }
+    for (int dev = 0; dev < kMaxDevices; ++dev) {
+        DeviceState &d = g_dev[dev];
+        if (!d.staged && !d.grid) continue;
+        cudaSetDevice(dev);
+        for (int k = 0; k < kSlots; ++k) {
+            if (d.slot[k]) cudaFree(d.slot[k]);
+            if (d.stream[k]) cudaStreamDestroy(d.stream[k]);
+            d.slot[k] = nullptr;
+            d.stream[k] = nullptr;
+        }
+        if (d.grid) cudaFree(d.grid);
+        if (d.scratch2) cudaFree(d.scratch2);
+        d.grid = nullptr; d.scratch2 = nullptr; d.grid_cells = 0; d.staged = false;
+    }
+    cudaSetDevice(prev);
+    return PTG_OK;
+}
+
+int ptg_selftest_div6(int64_t n, const double *in, double *out, void *stream) {
+    if (n < 0 || (n > 0 && (!in || !out))) return fail(PTG_EINVAL, "ptg_selftest_div6: bad arguments");
+    DeviceState *d;
+    int rc = current_device_state(&d);
+    if (rc) return rc;
+    PTG_CUDA(ptg::selftest_div6(n, in, out, (cudaStream_t)stream));
+    return PTG_OK;
+}
+
+}  // extern "C"

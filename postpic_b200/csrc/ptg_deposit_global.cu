@@ -1,0 +1,263 @@
+// ptg_deposit_global.cu -- deposit kernels that accumulate straight into the padded
+// grid in global memory with native fp64 reductions (RED.E.ADD.F64, resolved by the
+// L2 atomic units; the 8-137 MB grids of the target configurations are L2-resident
+// or nearly so on B200's 126 MB L2).
+//
+// Replaces the loops of /root/reference/postpic/particles/_particlestogrid.pyx
+// :70-129 (1-D), :181-276 (2-D), :341-463 (3-D).
+//
+//   method GLOBAL : one thread = one particle, one RED per stencil cell.  A warp-level
+//                   RED instruction then touches 32 unrelated 32-byte sectors.
+//   method ROWS   : the warp first evaluates 32 stencils, parks the (S+1)^(ndim-1)
+//                   rows of each in shared memory, then re-reads them so that the
+//                   lanes of one RED instruction cover whole stencil rows: S+1 adjacent
+//                   lanes hit S+1 adjacent doubles (one or two sectors) and the LSU
+//                   coalesces them into one L2 request per sector.
+#include "ptg_internal.cuh"
+
+namespace ptg {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;      // independent particle loads in flight per thread
+
+// ---------------------------------------------------------------------------------
+// one particle -> REDs (method GLOBAL)
+// ---------------------------------------------------------------------------------
+template <int ND, int S, bool W>
+__device__ __forceinline__ void deposit_particle_global(const DepositParams &P, double x, double y,
+                                                        double z, double w) {
+    if (S == 0) {
+        int cx = 0, cy = 0, cz = 0;
+        bool ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], cx);
+        if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], cy) && ok;
+        if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], cz) && ok;
+        if (!ok) return;
+        int64_t lin = cx;
+        if (ND >= 2) lin = lin * P.dims[1] + cy;
+        if (ND >= 3) lin = lin * P.dims[2] + cz;
+        red_add(P.grid + lin, W ? w : 1.0);
+        return;
+    }
+    constexpr int SS = S == 0 ? 1 : S;   // keeps the templates below well-formed for S == 0
+    constexpr int NW = SS + 1;
+    double wx[NW], wy[NW], wz[NW];
+    int bx = 0, by = 0, bz = 0;
+    bool ok = shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], bx, wx);
+    if (ND >= 2) ok = shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], by, wy) && ok;
+    if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], bz, wz) && ok;
+    if (!ok) return;
+    if (ND == 1) {
+        double *g = P.grid + bx;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) red_add(g + i, W ? __dmul_rn(wx[i], w) : wx[i]);
+    } else if (ND == 2) {
+        double *g = P.grid + (int64_t)bx * P.dims[1] + by;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+                const double c = __dmul_rn(wx[i], wy[j]);
+                red_add(g + j, W ? __dmul_rn(c, w) : c);
+            }
+            g += P.dims[1];
+        }
+    } else {
+        const int64_t sy = P.dims[2], sx = (int64_t)P.dims[1] * P.dims[2];
+        double *g = P.grid + bx * sx + by * sy + bz;
+#pragma unroll
+        for (int i = 0; i < NW; ++i)
+#pragma unroll
+            for (int j = 0; j < NW; ++j) {
+                const double cxy = __dmul_rn(wx[i], wy[j]);
+#pragma unroll
+                for (int k = 0; k < NW; ++k) {
+                    const double c = __dmul_rn(cxy, wz[k]);
+                    red_add(g + i * sx + j * sy + k, W ? __dmul_rn(c, w) : c);
+                }
+            }
+    }
+}
+
+template <int ND, int S, bool W>
+__global__ void __launch_bounds__(kThreads) k_deposit_global(const DepositParams P) {
+    const int64_t nthreads = (int64_t)gridDim.x * kThreads;
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
+    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2], sw = P.stride[3];
+    // main loop: kUnroll particles per thread with all loads issued before any use
+    for (; i + (kUnroll - 1) * nthreads < P.n; i += kUnroll * nthreads) {
+        double x[kUnroll], y[kUnroll], z[kUnroll], w[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const int64_t k = i + u * nthreads;
+            x[u] = ld_stream(px + k * sx);
+            y[u] = ND >= 2 ? ld_stream(py + k * sy) : 0.0;
+            z[u] = ND >= 3 ? ld_stream(pz + k * sz) : 0.0;
+            w[u] = W ? ld_stream(pw + k * sw) : 1.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) deposit_particle_global<ND, S, W>(P, x[u], y[u], z[u], w[u]);
+    }
+    for (; i < P.n; i += nthreads) {
+        const double x = ld_stream(px + i * sx);
+        const double y = ND >= 2 ? ld_stream(py + i * sy) : 0.0;
+        const double z = ND >= 3 ? ld_stream(pz + i * sz) : 0.0;
+        const double w = W ? ld_stream(pw + i * sw) : 1.0;
+        deposit_particle_global<ND, S, W>(P, x, y, z, w);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// method ROWS: sector-coalesced reductions
+// ---------------------------------------------------------------------------------
+// Lanes per row group (next power of two >= NW) and the padded per-particle stride of
+// the staging area, in doubles.  The stride is chosen so that the transposed read is
+// free of shared-memory bank conflicts within a 16-lane phase:
+//   NW = 2 (G = 2): 8 groups x 2 doubles  -> stride == 6 (mod 16) visits 0,6,12,2,8,14,4,10
+//   NW = 3,4 (G = 4): 4 groups x <=4 doubles -> stride == 4 or 12 (mod 16)
+template <int ND, int S> struct RowsCfg {
+    static constexpr int NW = S + 1;
+    static constexpr int G = NW == 2 ? 2 : 4;
+    static constexpr int ROWS = ND == 1 ? 1 : NW;          // rows per slab
+    static constexpr int SLABS = ND == 3 ? NW : 1;
+    static constexpr int K = ROWS * NW;                     // doubles staged per particle per slab
+    static constexpr int PS = NW == 2 ? (K <= 6 ? 6 : 22)   // K is 2 or 4
+                                      : (K <= 4 ? 4 : K <= 12 ? 12 : 20);
+    static constexpr int PPI = 32 / G;                      // particles per RED instruction
+    static constexpr int ITERS = ROWS * G;
+};
+
+template <int ND, int S, bool W>
+__global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P) {
+    using C = RowsCfg<ND, S>;
+    constexpr int NW = C::NW;
+    __shared__ __align__(16) double stage_all[(kThreads / 32) * 32 * C::PS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *stage = stage_all + warp * 32 * C::PS;
+    const int g = lane / C::G, j = lane % C::G;
+
+    const int64_t nthreads = (int64_t)gridDim.x * kThreads;
+    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
+    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2], sw = P.stride[3];
+    const int row_stride = ND == 1 ? 0 : P.dims[ND - 1];             // between rows of a slab
+    const int slab_stride = ND == 3 ? P.dims[1] * P.dims[2] : 0;
+
+    // warp-uniform trip count so that the warp-level exchanges stay convergent
+    const int64_t first = (int64_t)blockIdx.x * kThreads + warp * 32;
+    for (int64_t i0 = first; i0 < P.n; i0 += nthreads) {
+        const int64_t i = i0 + lane;
+        double wx[NW], wy[NW], wz[NW];
+        int bx = 0, by = 0, bz = 0;
+        double w = 1.0;
+        bool ok = i < P.n;
+        if (ok) {
+            const double x = ld_stream(px + i * sx);
+            const double y = ND >= 2 ? ld_stream(py + i * sy) : 0.0;
+            const double z = ND >= 3 ? ld_stream(pz + i * sz) : 0.0;
+            if (W) w = ld_stream(pw + i * sw);
+            ok = shape_axis<S, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], bx, wx);
+            if (ND >= 2) ok = shape_axis<S, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], by, wy) && ok;
+            if (ND >= 3) ok = shape_axis<S, (S == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], bz, wz) && ok;
+        }
+        int lin0 = -1;                                    // padded linear index of the first cell
+        if (ok) lin0 = ND == 1 ? bx : ND == 2 ? bx * P.dims[1] + by : (bx * P.dims[1] + by) * P.dims[2] + bz;
+
+#pragma unroll
+        for (int slab = 0; slab < C::SLABS; ++slab) {
+            if (ok) {
+                double *mine = stage + lane * C::PS;
+                if (ND == 1) {
+#pragma unroll
+                    for (int a = 0; a < NW; ++a) mine[a] = W ? __dmul_rn(wx[a], w) : wx[a];
+                } else if (ND == 2) {
+#pragma unroll
+                    for (int a = 0; a < NW; ++a)
+#pragma unroll
+                        for (int b = 0; b < NW; ++b) {
+                            const double c = __dmul_rn(wx[a], wy[b]);
+                            mine[a * NW + b] = W ? __dmul_rn(c, w) : c;
+                        }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < NW; ++a) {
+                        const double cxy = __dmul_rn(wx[slab], wy[a]);
+#pragma unroll
+                        for (int b = 0; b < NW; ++b) {
+                            const double c = __dmul_rn(cxy, wz[b]);
+                            mine[a * NW + b] = W ? __dmul_rn(c, w) : c;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < C::ITERS; ++it) {
+                const int row = it / C::G, pg = it % C::G;
+                const int p = pg * C::PPI + g;
+                const int l0 = __shfl_sync(0xffffffffu, lin0, p);
+                if (j < NW && l0 >= 0) {
+                    const double v = stage[p * C::PS + row * NW + j];
+                    red_add(P.grid + (int64_t)l0 + (int64_t)slab * slab_stride + row * row_stride + j, v);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------
+template <int ND, int S, bool W>
+static cudaError_t launch_global(const DepositParams &P, int sm_count, cudaStream_t st) {
+    if (P.n <= 0) return cudaSuccess;
+    int64_t want = (P.n + (int64_t)kThreads * kUnroll - 1) / ((int64_t)kThreads * kUnroll);
+    int64_t cap = (int64_t)sm_count * 8;                  // 8 x 256 threads = full occupancy
+    int blocks = (int)(want < cap ? want : cap);
+    if (blocks < 1) blocks = 1;
+    k_deposit_global<ND, S, W><<<blocks, kThreads, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <int ND, int S, bool W>
+static cudaError_t launch_rows(const DepositParams &P, int sm_count, cudaStream_t st) {
+    if (P.n <= 0) return cudaSuccess;
+    int64_t want = (P.n + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)sm_count * 8;
+    int blocks = (int)(want < cap ? want : cap);
+    if (blocks < 1) blocks = 1;
+    k_deposit_rows<ND, S, W><<<blocks, kThreads, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <int ND, int S>
+static cudaError_t dispatch_w(const DepositParams &P, bool rows, int sm_count, cudaStream_t st) {
+    const bool weighted = P.p[3] != nullptr;
+    if (rows) {
+        if constexpr (S >= 1) {
+            return weighted ? launch_rows<ND, S, true>(P, sm_count, st) : launch_rows<ND, S, false>(P, sm_count, st);
+        }
+    }
+    return weighted ? launch_global<ND, S, true>(P, sm_count, st) : launch_global<ND, S, false>(P, sm_count, st);
+}
+
+template <int ND>
+static cudaError_t dispatch_s(int shape, const DepositParams &P, bool rows, int sm_count, cudaStream_t st) {
+    switch (shape) {
+        case 0: return dispatch_w<ND, 0>(P, false, sm_count, st);
+        case 1: return dispatch_w<ND, 1>(P, rows, sm_count, st);
+        case 2: return dispatch_w<ND, 2>(P, rows, sm_count, st);
+        default: return dispatch_w<ND, 3>(P, rows, sm_count, st);
+    }
+}
+
+cudaError_t deposit_global(int ndim, int shape, const DepositParams &P, bool rows, int sm_count,
+                           cudaStream_t st) {
+    switch (ndim) {
+        case 1: return dispatch_s<1>(shape, P, rows, sm_count, st);
+        case 2: return dispatch_s<2>(shape, P, rows, sm_count, st);
+        default: return dispatch_s<3>(shape, P, rows, sm_count, st);
+    }
+}
+
+}  // namespace ptg

@@ -1,0 +1,125 @@
+// ptg_stencil.cuh -- per-axis shape-function evaluation, in registers.
+//
+// Restates the arithmetic of /root/reference/postpic/particles/_particlestogrid.pyx
+// (1-D: :71-129, 2-D: :182-276, 3-D: :342-463) for one axis.  Every floating-point
+// operation is written with an explicit round-to-nearest intrinsic (__dadd_rn,
+// __dmul_rn ...) so that nvcc can never contract a multiply and an add into an FMA:
+// the reference build (gcc -O2, baseline x86-64) contains no FMA, and a fused
+// `u + 0.5` right after the scaling multiply could move a particle that sits within
+// one ulp of a cell boundary into the neighbouring cell.  With this, the contribution
+// of every particle to every cell is bit-identical to the reference's; only the
+// order in which contributions are summed differs.
+#pragma once
+#include <cstdint>
+
+namespace ptg {
+
+// Number of stencil cells along one axis.
+template <int S> struct StencilWidth { static constexpr int value = S + 1; };
+template <> struct StencilWidth<0> { static constexpr int value = 1; };
+
+// x / 6 correctly rounded without the ~30-instruction IEEE division sequence:
+// q = RN(x * RN(1/6)); r = x - 6 q (exact in an FMA); result = RN(q + r * RN(1/6)).
+// (Markstein's correction step; checked bit-for-bit against `/ 6.0` by
+// tests/test_gpu_parity.py::test_div6_bit_exact through ptg_selftest_div6.)
+__device__ __forceinline__ double div6(double x) {
+    const double y = 1.0 / 6.0;
+    const double q = __dmul_rn(x, y);
+    const double r = __fma_rn(-6.0, q, x);
+    return __fma_rn(r, y, q);
+}
+
+// Scaled coordinate u = (d - lo) * inv  (pyx:71, :182-183, :342-344 ...).
+__device__ __forceinline__ double scaled(double d, double lo, double inv) {
+    return __dmul_rn(__dsub_rn(d, lo), inv);
+}
+
+// Shape 0 (NGP) on one axis: accept iff u > 0 and u < bins (both strict; pyx:72, :184,
+// :345); cell = trunc(u).  NaN fails both comparisons.
+__device__ __forceinline__ bool ngp_axis(double d, double lo, double inv, double fbins, int &cell) {
+    const double u = scaled(d, lo, inv);
+    const bool ok = (u > 0.0) && (u < fbins);
+    cell = ok ? __double2int_rz(u) : 0;
+    return ok;
+}
+
+// Shapes 1..3 on one axis.
+//   ON_DOUBLE = false : the reference tests the truncated int, `r >= 0 and r <= bins`
+//                       (x always; z for 3-D shapes 2,3; pyx:85,:101,:119,:200,:228,:258,:399,:438)
+//   ON_DOUBLE = true  : the reference tests the raw double on the left, `u >= 0 and r <= bins`
+//                       (y always; z for 3-D shape 1; pyx:200,:228,:258,:363)
+// The int tests are evaluated in the double domain (trunc(v) >= 0 <=> v > -1,
+// trunc(v) <= bins <=> v < bins + 1), which gives x86's outcome for NaN / inf / |v| >= 2^31
+// on an int-tested axis (cvttsd2si -> INT_MIN -> rejected) and DROPS the particles for
+// which the reference runs into undefined behaviour on a double-tested axis.
+// base = first padded cell index; wt[0..S] = stencil weights.
+template <int S, bool ON_DOUBLE>
+__device__ __forceinline__ bool shape_axis(double d, double lo, double inv, double fbins_p1,
+                                           int &base, double (&wt)[S + 1]) {
+    static_assert(S >= 1 && S <= 3, "shape order");
+    const double u = scaled(d, lo, inv);
+    const double v = (S == 2) ? u : __dadd_rn(u, 0.5);
+    bool ok = v < fbins_p1;
+    if (ON_DOUBLE) ok = ok && (u >= 0.0);
+    else           ok = ok && (v > -1.0);
+    if (!ok) { base = 0; return false; }
+    const int r = __double2int_rz(v);
+    const double rd = __int2double_rn(r);
+    if (S == 1) {
+        wt[0] = __dadd_rn(__dsub_rn(0.5, u), rd);        // (0.5 - u) + r   pyx:88,:201
+        wt[1] = __dsub_rn(__dadd_rn(0.5, u), rd);        // (0.5 + u) - r   pyx:87,:202
+        base = r;
+    } else if (S == 2) {
+        const double t = __dsub_rn(u, rd);               // pyx:100,:226
+        const double omt = __dsub_rn(1.0, t);
+        const double tt = __dmul_rn(t, t);
+        wt[0] = __dmul_rn(0.5, __dmul_rn(omt, omt));     // 0.5*(1-t)^2     pyx:103,:229
+        wt[1] = __dsub_rn(__dadd_rn(0.5, t), tt);        // 0.5 + t - t^2   pyx:104,:230
+        wt[2] = __dmul_rn(0.5, tt);                      // 0.5*t^2         pyx:105,:231
+        base = r + 1;
+    } else {
+        const double t = __dadd_rn(__dsub_rn(u, rd), 0.5);   // pyx:118,:256
+        const double sixth = 1.0 / 6.0, twothirds = 2.0 / 3.0;
+        const double th = __dmul_rn(t, 0.5);                 // t/2 (exact)
+        // 1/6 + t*(-0.5 + (0.5 - t/6)*t)                       pyx:121,:259
+        wt[0] = __dadd_rn(sixth, __dmul_rn(t, __dadd_rn(-0.5, __dmul_rn(__dsub_rn(0.5, div6(t)), t))));
+        // 2/3 + (-1 + t/2)*t*t                                 pyx:122,:260
+        wt[1] = __dadd_rn(twothirds, __dmul_rn(__dmul_rn(__dadd_rn(-1.0, th), t), t));
+        // 1/6 + t*(0.5 + (0.5 - t/2)*t)                        pyx:123,:261
+        wt[2] = __dadd_rn(sixth, __dmul_rn(t, __dadd_rn(0.5, __dmul_rn(__dsub_rn(0.5, th), t))));
+        // t*t*t/6                                              pyx:124,:262
+        wt[3] = div6(__dmul_rn(__dmul_rn(t, t), t));
+        base = r + 1;
+    }
+    return true;
+}
+
+// Everything a deposit kernel needs to know about the job (passed by value as the
+// kernel argument: lives in the constant bank, costs no registers until used).
+struct DepositParams {
+    const double *p[4];     // x, y, z, w   (w may be null)
+    int64_t stride[4];      // element strides
+    int64_t n;
+    double lo[3], inv[3];
+    double fbins[3];        // (double) bins
+    double fbins_p1[3];     // (double) bins + 1.0
+    int bins[3];
+    int dims[3];            // padded dims = bins + 2*shape
+    double *grid;
+};
+
+// Streaming 8-byte load: read-only path, do not allocate in L1 (each particle is
+// touched exactly once).
+__device__ __forceinline__ double ld_stream(const double *p) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// Fire-and-forget fp64 reduction into global memory: a single native
+// RED.E.ADD.F64.RN.STRONG.GPU, resolved by the L2 atomic units.
+__device__ __forceinline__ void red_add(double *addr, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+}  // namespace ptg

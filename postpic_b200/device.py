@@ -1,0 +1,134 @@
+"""Device-resident face of the deposition library.
+
+`deposit()` takes 1-D float64 CUDA tensors (zero-copy, `tensor.data_ptr()` goes
+straight into the C ABI) and returns the ghost-padded grid as a CUDA tensor, so a
+caller that already has its particles in HBM never crosses PCIe.  PyTorch is used for
+device memory, streams and (in `postpic_b200.parallel`) torch.distributed only; all
+arithmetic happens in libptg_b200.so.
+
+Replaces the loops of /root/reference/postpic/particles/_particlestogrid.pyx
+(:70-129, :181-276, :341-463); set-up arithmetic in `_setup.py`.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._setup import shape_order, axis_setup, as_bins
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def is_cuda_tensor(a):
+    return type(a).__module__.split('.')[0] == 'torch' and getattr(a, 'is_cuda', False)
+
+
+def _check_tensor(t, name):
+    torch = _torch()
+    if t.dtype != torch.float64:
+        raise ValueError("Buffer dtype mismatch, expected 'double_t' but got '{}' ({})".format(t.dtype, name))
+    if t.dim() != 1:
+        raise ValueError('Buffer has wrong number of dimensions (expected 1, got {})'.format(t.dim()))
+    if t.numel() > 1 and t.stride(0) < 1:
+        raise ValueError('{}: negative or zero strides are not supported on device tensors'.format(name))
+
+
+class Plan(object):
+    """Everything about a histogram except the particles: shape order, bins, lo/inv/edges."""
+
+    def __init__(self, ranges, bins, shape):
+        self.ndim = len(ranges)
+        if not 1 <= self.ndim <= 3:
+            raise ValueError('only 1, 2 or 3 axes are supported')
+        self.shape = shape_order(shape)
+        self.bins = [int(b) for b in bins]
+        if len(self.bins) != self.ndim:
+            raise ValueError('need one bin count per axis')
+        self.lo = np.zeros(3)
+        self.inv = np.ones(3)
+        self.edges = []
+        for a in range(self.ndim):
+            self.lo[a], self.inv[a], e = axis_setup(ranges[a], self.bins[a])
+            self.edges.append(e)
+        self.dims = [b + 2 * self.shape for b in self.bins]
+        self.cells = int(np.prod(self.dims, dtype=np.int64))
+        self.cbins = (ctypes.c_int * 3)(*(self.bins + [1] * (3 - self.ndim)))
+        self.interior = tuple(slice(self.shape, self.shape + b) for b in self.bins)
+
+    def cell_volume(self):
+        """prod(edge[1] - edge[0]) -- the dV of particles.py:1101."""
+        return float(np.prod([e[1] - e[0] for e in self.edges]))
+
+
+def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, stream=None):
+    """Deposit CUDA tensors `coords` (+ optional `weights`) into the padded CUDA tensor `grid`.
+
+    Asynchronous on `stream` (default: torch's current stream on grid.device)."""
+    torch = _torch()
+    lib = _lib.load()
+    if len(coords) != plan.ndim:
+        raise ValueError('expected {} coordinate arrays'.format(plan.ndim))
+    n = coords[0].numel()
+    for t, nm in zip(coords, 'xyz'):
+        _check_tensor(t, 'data' + nm)
+        if t.numel() != n:
+            raise ValueError('datax and data{} must be of equal length'.format(nm))
+        if t.device != grid.device:
+            raise ValueError('all tensors must live on the same device')
+    if weights is not None:
+        _check_tensor(weights, 'weights')
+        if weights.numel() < n:
+            raise ValueError('weights must have at least as many elements as data')
+    if grid.dtype != torch.float64 or not grid.is_contiguous() or grid.numel() != plan.cells:
+        raise ValueError('grid must be a contiguous float64 tensor of {} elements'.format(plan.cells))
+    ptr = [t.data_ptr() if n else None for t in coords] + [None] * (3 - plan.ndim)
+    strides = [t.stride(0) if n > 1 else 1 for t in coords] + [1] * (3 - plan.ndim)
+    ptr.append(weights.data_ptr() if (weights is not None and n) else None)
+    strides.append(weights.stride(0) if (weights is not None and n > 1) else 1)
+    cstr = (ctypes.c_int64 * 4)(*strides)
+    flags = _lib.METHODS[method] | (_lib.ZERO_GRID if zero else 0)
+    with torch.cuda.device(grid.device):
+        st = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _lib.check(lib.ptg_deposit_f64(plan.ndim, plan.shape, n, ptr[0], ptr[1], ptr[2], ptr[3], cstr,
+                                       plan.lo.ctypes.data, plan.inv.ctypes.data, plan.cbins,
+                                       grid.data_ptr(), flags, None, 0, st))
+    return grid
+
+
+def deposit(coords, weights=None, range=None, bins=None, shape=0, method=None):
+    """-> (padded grid CUDA tensor, plan).  `plan.interior` slices out the histogram."""
+    torch = _torch()
+    coords = list(coords)
+    nd = len(coords)
+    if nd == 1 and np.isscalar(range[0]):
+        range = [range]
+    plan = Plan(range, as_bins(bins[0] if (nd == 1 and np.ndim(bins)) else bins, nd), shape)
+    grid = torch.empty(plan.dims, dtype=torch.float64, device=coords[0].device)
+    deposit_into(grid, plan, coords, weights, method=method, zero=True)
+    return grid, plan
+
+
+def minmax(t):
+    """(min, max) of a 1-D float64 CUDA tensor as Python floats (NaN propagates like numpy)."""
+    torch = _torch()
+    _check_tensor(t, 'data')
+    if t.numel() == 0:
+        raise ValueError('zero-size array to reduction operation minimum which has no identity')
+    out = torch.empty(2, dtype=torch.float64, device=t.device)
+    with torch.cuda.device(t.device):
+        _lib.check(_lib.load().ptg_minmax_f64(t.numel(), t.data_ptr(), t.stride(0) if t.numel() > 1 else 1,
+                                              out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    lo, hi = out.tolist()
+    return lo, hi
+
+
+def scale_(grid, factor):
+    """grid *= factor in place on the device (the h /= dV of particles.py:1102 with factor = 1/dV)."""
+    torch = _torch()
+    with torch.cuda.device(grid.device):
+        _lib.check(_lib.load().ptg_scale_f64(grid.data_ptr(), grid.numel(), float(factor),
+                                             torch.cuda.current_stream().cuda_stream))
+    return grid

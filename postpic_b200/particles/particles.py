@@ -1,0 +1,344 @@
+"""The histogram dispatch of `MultiSpecies` -- and only that.
+
+Re-states the contract of
+    MultiSpecies._createHistgram   /root/reference/postpic/particles/particles.py:1015-1103
+    MultiSpecies.createField       /root/reference/postpic/particles/particles.py:1105-1167
+(plus the historic `createHistgram1d/2d/3d` names, which that checkout merged into
+`_createHistgram`) on top of the CUDA `histogramdd`.  Everything else `MultiSpecies`
+does in postpic (species bookkeeping, compress/filter, particle tracking, file
+readers, the plotting `Field` with its 2000 lines of methods) is out of scope; the
+small stand-ins here (`ArraySource`, `Field`, the scalar table) exist so the dispatch
+can be exercised and tested without postpic installed.  When postpic is installed, a
+maintainer swaps one import instead.
+
+Per-particle scalars are evaluated with numpy for host arrays and with torch ops for
+CUDA tensors, so a device-resident particle set never leaves HBM before deposition.
+"""
+import warnings
+
+import numpy as np
+
+from ._routines import histogramdd
+from .. import device as _device
+
+__all__ = ['MultiSpecies', 'Field', 'ArraySource']
+
+try:                                     # the reference resolves unknown names in scipy.constants
+    import scipy.constants as _sc       # (particles.py:303,:322)
+except ImportError:                      # pragma: no cover
+    _sc = None
+
+# fallback table when scipy is absent (CODATA values of the names the default scalars use)
+_CONSTANTS = {
+    'c': 299792458.0,
+    'elementary_charge': 1.602176634e-19,
+    'atomic_mass': 1.66053906660e-27,
+    'electron_mass': 9.1093837015e-31,
+    'pi': np.pi,
+}
+
+# name -> (expression in terms of other scalars, unit).  The definitions are those of
+# postpic's default scalar context (scalarproperties.py:159-222); written as data.
+_SCALARS = {
+    'w': ('weight', 'npartpermacro'), 'm': ('mass', 'kg'), 'q': ('charge', 'C'),
+    'mass_u': ('mass / atomic_mass', 'amu'), 'm_u': ('mass / atomic_mass', 'amu'),
+    'charge_e': ('charge / elementary_charge', ''), 'q_e': ('charge / elementary_charge', ''),
+    'x_um': ('x * 1e6', r'$\mu$ m'), 'y_um': ('y * 1e6', r'$\mu$ m'), 'z_um': ('z * 1e6', r'$\mu$ m'),
+    'p': ('sqrt(px**2 + py**2 + pz**2)', 'kg*m/s'),
+    '_np2': ('(px**2 + py**2 + pz**2)/(mass * c)**2', ''),
+    'gamma_m1': ('_np2 / (sqrt(1 + _np2) + 1)', ''),
+    'gamma': ('_np2 / (sqrt(1 + _np2) + 1) + 1', ''),
+    'gamma_m': ('gamma * mass', 'kg'),
+    'beta': ('sqrt(gamma_m1**2 + 2 * gamma_m1) / (gamma_m1 + 1)', ''),
+    'v': ('beta * c', 'm/s'),
+    'vx': ('px / (gamma * mass)', 'm/s'), 'vy': ('py / (gamma * mass)', 'm/s'), 'vz': ('pz / (gamma * mass)', 'm/s'),
+    'betax': ('vx / c', ''), 'betay': ('vy / c', ''), 'betaz': ('vz / c', ''),
+    'Eruhe': ('mass * c**2', 'J'),
+    'Ekin': ('gamma_m1 * mass * c**2', 'J'),
+    'Ekin_MeV': ('Ekin / elementary_charge / 1e6', 'MeV'),
+    'Ekin_MeV_amu': ('Ekin / elementary_charge / 1e6 / mass_u', 'MeV/u'),
+    'Ekin_keV': ('Ekin / elementary_charge / 1e3', 'keV'),
+    'Ekin_keV_amu': ('Ekin / elementary_charge / 1e3 / mass_u', 'keV/u'),
+    'angle_xy': ('arctan2(py, px)', 'rad'), 'angle_yx': ('arctan2(px, py)', 'rad'),
+    'angle_yz': ('arctan2(pz, py)', 'rad'), 'angle_zy': ('arctan2(py, pz)', 'rad'),
+    'angle_zx': ('arctan2(px, pz)', 'rad'), 'angle_xz': ('arctan2(pz, px)', 'rad'),
+    'r_xy': ('sqrt(x**2 + y**2)', 'm'), 'r_yz': ('sqrt(y**2 + z**2)', 'm'),
+    'r_zx': ('sqrt(z**2 + x**2)', 'm'), 'r_xyz': ('sqrt(x**2 + y**2 + z**2)', 'm'),
+}
+_ATOMIC_UNITS = {'x': 'm', 'y': 'm', 'z': 'm', 'px': 'kg*m/s', 'py': 'kg*m/s', 'pz': 'kg*m/s',
+                 'weight': 'npartpermacro', 'mass': 'kg', 'charge': 'C', 'id': '', 'time': 's'}
+
+
+def _unit_of(expr):
+    if expr in _ATOMIC_UNITS:
+        return _ATOMIC_UNITS[expr]
+    if expr in _SCALARS:
+        return _SCALARS[expr][1]
+    return ''
+
+
+class ArraySource(object):
+    """One species worth of particles held as arrays (numpy, or torch CUDA tensors).
+
+    Stand-in for a `_SingleSpecies` bound to a dumpreader (particles.py:60-340): it
+    answers `atomic(name)` with a 1-D float64 array of length `len(self)`; scalars
+    given as Python numbers (e.g. mass=9.1e-31, weight=1.0) are broadcast lazily.
+    `extent` maps an axis name to (lo, hi) -- the reader's `simextent(axis)`.
+    """
+
+    def __init__(self, species, arrays, extent=None):
+        self.species = species
+        self._arrays = dict(arrays)
+        self.extent = dict(extent or {})
+        lens = [len(v) for v in self._arrays.values() if np.ndim(v) == 1 or _device.is_cuda_tensor(v)]
+        if not lens:
+            raise ValueError('at least one per-particle array is required')
+        if len(set(lens)) != 1:
+            raise ValueError('all per-particle arrays of a species must have equal length')
+        self._n = lens[0]
+        sample = [v for v in self._arrays.values() if _device.is_cuda_tensor(v)]
+        self.device = sample[0].device if sample else None
+
+    def __len__(self):
+        return self._n
+
+    def atomic(self, name):
+        if name not in self._arrays:
+            raise KeyError(name)
+        v = self._arrays[name]
+        if _device.is_cuda_tensor(v):
+            return v
+        if np.ndim(v) == 0:
+            if self.device is not None:
+                torch = _device._torch()
+                return torch.full((self._n,), float(v), dtype=torch.float64, device=self.device)
+            return np.full(self._n, float(v), dtype=np.float64)
+        return np.asarray(v, dtype=np.float64)
+
+
+class _Namespace(dict):
+    """Name resolution for `eval`: atomic arrays, derived scalars (recursively), constants."""
+
+    def __init__(self, source, funcs):
+        dict.__init__(self)
+        self._source = source
+        self.update(funcs)
+
+    def __missing__(self, key):
+        if key in _SCALARS:
+            val = eval(_SCALARS[key][0], {'__builtins__': {}}, self)      # noqa: S307 (own table)
+        else:
+            try:
+                val = self._source.atomic(key)
+            except KeyError:
+                if _sc is not None and isinstance(getattr(_sc, key, None), float):
+                    val = getattr(_sc, key)
+                elif key in _CONSTANTS:
+                    val = _CONSTANTS[key]
+                else:
+                    raise
+        self[key] = val
+        return val
+
+
+def _numpy_funcs():
+    return {k: getattr(np, k) for k in ('sqrt', 'arctan2', 'sin', 'cos', 'tan', 'exp', 'log', 'abs', 'where')}
+
+
+def _torch_funcs():
+    torch = _device._torch()
+    return {'sqrt': torch.sqrt, 'arctan2': torch.atan2, 'sin': torch.sin, 'cos': torch.cos, 'tan': torch.tan,
+            'exp': torch.exp, 'log': torch.log, 'abs': torch.abs, 'where': torch.where}
+
+
+class Field(object):
+    """Minimal result container with the constructor contract of postpic's `Field`
+    (datahandling.py:561-612): `Field(matrix, xedges=..., yedges=..., zedges=...)`
+    keeps `np.asarray(matrix)` and one edge array per axis."""
+
+    class _Axis(object):
+        def __init__(self, grid_node):
+            self.grid_node = np.asarray(grid_node)
+            self.name = ''
+            self.unit = ''
+
+        @property
+        def grid(self):
+            return 0.5 * (self.grid_node[1:] + self.grid_node[:-1])
+
+        @property
+        def extent(self):
+            return [self.grid_node[0], self.grid_node[-1]]
+
+    def __init__(self, matrix, xedges=None, yedges=None, zedges=None, name='', unit=''):
+        self.matrix = np.asarray(matrix)
+        self.axes = [Field._Axis(e) for e in (xedges, yedges, zedges) if e is not None]
+        if len(self.axes) != self.matrix.ndim:
+            raise ValueError('one edge array per matrix dimension is required')
+        self.name = name
+        self.unit = unit
+        self.label = ''
+        self.infostring = ''
+        self.infos = []
+
+    @property
+    def shape(self):
+        return self.matrix.shape
+
+    @property
+    def dimensions(self):
+        return self.matrix.ndim
+
+    @property
+    def extent(self):
+        return [v for ax in self.axes for v in ax.extent]
+
+    def __array__(self, dtype=None, copy=None):
+        return np.asarray(self.matrix, dtype=dtype)
+
+
+class MultiSpecies(object):
+    """A collection of particle species exposing postpic's histogram entry points."""
+
+    def __init__(self, *sources):
+        self._sources = list(sources)
+
+    # -- the small part of the container API the dispatch below relies on ----------
+    @property
+    def npart(self):
+        return sum(len(s) for s in self._sources)
+
+    @property
+    def nspecies(self):
+        return len(self._sources)
+
+    @property
+    def species(self):
+        names = sorted(set(s.species for s in self._sources))
+        return ' '.join(names)
+
+    def __len__(self):
+        return self.npart
+
+    def __add__(self, other):
+        return MultiSpecies(*(self._sources + other._sources))
+
+    def getcompresslog(self):
+        return {'all': []}
+
+    def simextent(self, axis):
+        """Combined extent of all species for `axis`, or None (particles.py:396-404)."""
+        ext = [s.extent[axis] for s in self._sources if axis in s.extent]
+        if not ext or len(ext) != len(self._sources):
+            return None
+        return np.asarray([min(e[0] for e in ext), max(e[1] for e in ext)])
+
+    def simgridpoints(self, axis):
+        """Always None: the reference's method computes a value but never returns it
+        (particles.py:407-416), so `simgrid=True` only implies `simextent=True`."""
+        return None
+
+    def __call__(self, expr):
+        """Evaluate a scalar expression per particle and concatenate over species
+        (particles.py:626-674)."""
+        if callable(expr):
+            return expr(self)
+        expr = getattr(expr, 'symbol', expr)
+        parts = []
+        for s in self._sources:
+            funcs = _torch_funcs() if s.device is not None else _numpy_funcs()
+            ns = _Namespace(s, funcs)
+            val = eval(str(expr), {'__builtins__': {}}, ns)              # noqa: S307
+            if np.ndim(val) == 0 and not _device.is_cuda_tensor(val):
+                val = s.atomic('weight') * 0 + float(val) if 'weight' in s._arrays else np.full(len(s), float(val))
+            parts.append(val)
+        if not parts:
+            return np.empty(0, dtype=np.float64)
+        if len(parts) == 1:
+            return parts[0]
+        if _device.is_cuda_tensor(parts[0]):
+            return _device._torch().cat(parts)
+        return np.hstack(parts)
+
+    # -- the dispatch ------------------------------------------------------------------
+    def _createHistgram(self, *sps, **kwargs):
+        """(h, edges) of a 1-, 2- or 3-D deposit of this particle collection, divided by
+        the cell volume.  Keywords: simextent, simgrid, rangex/rangey/rangez, weights
+        (default '1'), force, bins, shape (particles.py:1015-1103)."""
+        if 'optargsh' in kwargs:
+            warnings.warn('keyword "optargsh" is deprecated. Use "bins" and "shape" '
+                          'arguments directly on "createField".', category=DeprecationWarning)
+            kwargs.update(kwargs.pop('optargsh'))
+        simextent = kwargs.pop('simextent', False)
+        simgrid = kwargs.pop('simgrid', False)
+        ranges = [kwargs.pop('rangex', None), kwargs.pop('rangey', None), kwargs.pop('rangez', None)]
+        weights = kwargs.pop('weights', '1')
+        force = kwargs.pop('force', False)
+        bins = kwargs.pop('bins', None)
+        shape = kwargs.pop('shape', None)
+        if len(kwargs) > 0:
+            raise TypeError("got an unexpected keyword argument {}'".format(kwargs))
+        if len(sps) > 3:
+            raise TypeError('Only 1D, 2D or 3D Histograms can be created.')
+
+        if simgrid:
+            simextent = True
+        try:
+            data = [self(sp) for sp in sps]
+        except KeyError:
+            if not force:
+                raise
+            data = [[]]
+        if simextent:
+            for i, sp in enumerate(sps):
+                tmp = self.simextent(getattr(sp, 'symbol', sp))
+                ranges[i] = tmp if tmp is not None else ranges[i]
+        if simgrid:
+            for i, sp in enumerate(sps):
+                tmp = self.simgridpoints(getattr(sp, 'symbol', sp))
+                if tmp is not None:
+                    bins[i] = tmp
+        if len(data[0]) == 0:                       # no particles: an all-zero histogram
+            h = np.zeros(bins)
+
+            def edges_of(r, nb):
+                return np.linspace(r[0], r[1], nb + 1) if r is not None else np.linspace(0, 1, nb + 1)
+            edges = [edges_of(r, bins[i]) for i, r in zip(range(h.ndim), ranges)]
+            return h, edges
+
+        w = self('weight * ({})'.format(weights))
+        h, edges = histogramdd(data, weights=w, range=ranges, bins=bins, shape=shape)
+        dV = np.prod([edge[1] - edge[0] for edge in edges])
+        h /= dV
+        return h, edges
+
+    def createHistgram1d(self, spx, **kwargs):
+        return self._createHistgram(spx, **kwargs)
+
+    def createHistgram2d(self, spx, spy, **kwargs):
+        return self._createHistgram(spx, spy, **kwargs)
+
+    def createHistgram3d(self, spx, spy, spz, **kwargs):
+        return self._createHistgram(spx, spy, spz, **kwargs)
+
+    def createField(self, *sps, **kwargs):
+        """n-d histogram wrapped in a `Field` with names/units filled in
+        (particles.py:1105-1167).  Extra keywords: name (default 'distfn'), title."""
+        name = kwargs.pop('name', 'distfn')
+        title = kwargs.pop('title', None)
+        h, edges = self._createHistgram(*sps, **kwargs)
+        edgekw = {k: e for k, e in zip(['xedges', 'yedges', 'zedges'], edges)}
+        ret = Field(h, **edgekw)
+        if 'weights' in kwargs:
+            name = getattr(kwargs['weights'], 'name', kwargs['weights'])
+            name = name if isinstance(name, str) else 'distfn'
+        ret.name = str(name) + self.species
+        ret.label = self.species
+        ret.name = title if title else ret.name
+        for i, sp in enumerate(sps):
+            sym = getattr(sp, 'symbol', sp)
+            ret.axes[i].unit = getattr(sp, 'unit', _unit_of(sym))
+            ret.axes[i].name = getattr(sp, 'name', sym if isinstance(sym, str) else '')
+        ret.infostring = '{:.0f} npart in {:.0f} species'.format(self.npart, self.nspecies)
+        ret.infos = self.getcompresslog()['all']
+        return ret
