@@ -44,7 +44,7 @@ def axis_setup(rng, bins):
         hi += s
         lo -= s
     edges = np.linspace(lo, hi, bins + 1)
-    with np.errstate(divide='ignore', invalid='ignore'):
+    with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
         inv = float(np.float64(1.0) / np.float64(hi - lo) * bins)
     return lo, inv, edges
 

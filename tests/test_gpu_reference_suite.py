@@ -1,0 +1,210 @@
+"""The reference's own hot-path tests (test/test_particlestogrid.py, test/test_particles.py:37-49)
+re-hosted on the CUDA drop-in: same calls, same assertions, seeded data."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cf():
+    from postpic_b200.particles import _particlestogrid
+    _particlestogrid.method = None
+    return _particlestogrid
+
+
+@pytest.fixture(scope="module")
+def histogramdd():
+    from postpic_b200.particles import histogramdd
+    return histogramdd
+
+
+class TestHistogram:
+    @pytest.fixture(autouse=True)
+    def _data(self):
+        rng = np.random.default_rng(11)
+        self.data = rng.random(int(1e5))
+        self.weights = rng.random(int(1e5))
+
+    def test_histogram(self, cf):
+        cfh, cfe = cf.histogram(self.data, bins=20, range=(0, 1), shape=0)
+        nph, npe = np.histogram(self.data, bins=20, range=(0, 1))
+        assert list(nph) == list(cfh)
+        assert list(npe) == list(cfe)
+
+    def test_histogramw(self, cf):
+        cfh, cfe = cf.histogram(self.data, bins=100, range=(0, 1), shape=0, weights=self.weights)
+        nph, npe = np.histogram(self.data, bins=100, range=(0, 1), weights=self.weights)
+        assert abs(np.sum(np.abs(cfh - nph))) < 5e-8
+        assert list(npe) == list(cfe)
+
+    @pytest.mark.parametrize("shape", [1, 2, 3])
+    @pytest.mark.parametrize("weighted", [False, True])
+    def test_histogram_orders(self, cf, shape, weighted):
+        w = self.weights if weighted else None
+        cfh, cfe = cf.histogram(self.data, bins=100, range=(0.0, 1.0), shape=shape, weights=w)
+        nph, npe = np.histogram(self.data, bins=100, range=(0.0, 1.0), weights=w)
+        totalmass = np.sum(w) if weighted else len(self.data)
+        assert abs(np.sum(cfh.base) - totalmass) < 5e-8      # cfh.base includes the ghost cells
+        assert list(npe) == list(cfe)
+
+
+class TestHistogram2d3d:
+    @pytest.fixture(autouse=True)
+    def _data(self):
+        rng = np.random.default_rng(12)
+        self.datax = rng.random(1000)
+        self.datay = 2 * rng.random(1000)
+        self.dataz = 3 * rng.random(1000)
+        self.weights = rng.random(1000)
+
+    @pytest.mark.parametrize("shape", [0, 1, 2, 3])
+    @pytest.mark.parametrize("weighted", [False, True])
+    def test_histogram2d(self, cf, shape, weighted):
+        w = self.weights if weighted else None
+        cfh, cfex, cfey = cf.histogram2d(self.datax, self.datay, weights=w, bins=(20, 30),
+                                         range=((0, 1), (0, 2)), shape=shape)
+        nph, npex, npey = np.histogram2d(self.datax, self.datay, weights=w, bins=(20, 30), range=((0, 1), (0, 2)))
+        totalmass = np.sum(w) if weighted else len(self.datax)
+        assert abs(np.sum(cfh.base) - totalmass) < 5e-8
+        assert list(npex) == list(cfex) and list(npey) == list(cfey)
+        if shape == 0:
+            assert np.allclose(cfh, nph)
+
+    @pytest.mark.parametrize("shape", [0, 1, 2, 3])
+    @pytest.mark.parametrize("weighted", [False, True])
+    def test_histogram3d(self, cf, shape, weighted):
+        w = self.weights if weighted else None
+        cfh, ex, ey, ez = cf.histogram3d(self.datax, self.datay, self.dataz, weights=w, bins=(20, 30, 40),
+                                         range=((0, 1), (0, 2), (0, 3)), shape=shape)
+        totalmass = np.sum(w) if weighted else len(self.datax)
+        assert abs(np.sum(cfh.base) - totalmass) < 5e-8
+
+
+class TestHistogramdd:
+    @pytest.fixture(autouse=True)
+    def _data(self):
+        rng = np.random.default_rng(13)
+        self.datax = rng.random(1000)
+        self.datay = 2 * rng.random(1000)
+        self.dataz = 3 * rng.random(1000)
+        self.weights = rng.random(1000)
+
+    def test_histogram1d_call_forms(self, histogramdd):
+        h0, (ex0,) = histogramdd(self.datax, bins=20, range=(0, 1), shape=0)
+        forms = [histogramdd((self.datax,), bins=20, range=((0, 1),), shape=0),
+                 histogramdd((self.datax,), bins=20, range=(0, 1), shape=0),
+                 histogramdd(self.datax, bins=20, range=((0, 1),), shape=0),
+                 histogramdd(self.datax, bins=(20,), range=((0, 1),), shape=0)]
+        for h, (ex,) in forms:
+            assert np.all(np.isclose(h0, h)) and np.all(np.isclose(ex0, ex))
+
+    def test_against_numpy_1d(self, histogramdd):
+        h0, (ex0,) = histogramdd(self.datax, bins=20, range=(0, 1), shape=0)
+        h1, (ex1,) = np.histogramdd(self.datax, bins=20, range=((0, 1),))
+        assert np.all(np.isclose(h0, h1)) and np.all(np.isclose(ex0, ex1))
+        assert abs(np.sum(h0) - len(self.datax)) < 1e-7
+
+    @pytest.mark.parametrize("weighted", [False, True])
+    def test_against_numpy_2d_3d(self, histogramdd, weighted):
+        w = self.weights if weighted else None
+        total = np.sum(w) if weighted else len(self.datax)
+        arg = (self.datax, self.datay)
+        h0, e0 = histogramdd(arg, bins=[20, 22], range=((0, 1), (0, 2)), shape=0, weights=w)
+        h1, e1 = np.histogramdd(arg, bins=[20, 22], range=((0, 1), (0, 2)), weights=w)
+        assert np.all(np.isclose(h0, h1)) and all(np.all(np.isclose(a, b)) for a, b in zip(e0, e1))
+        assert abs(np.sum(h0) - total) < 1e-7
+        arg = (self.datax, self.datay, self.dataz)
+        h0, e0 = histogramdd(arg, bins=[20, 22, 25], range=((0, 1), (0, 2), (0, 3)), shape=0, weights=w)
+        h1, e1 = np.histogramdd(arg, bins=[20, 22, 25], range=((0, 1), (0, 2), (0, 3)), weights=w)
+        assert np.all(np.isclose(h0, h1)) and all(np.all(np.isclose(a, b)) for a, b in zip(e0, e1))
+        assert abs(np.sum(h0) - total) < 1e-7
+
+    def test_nd_array_form_and_scalar_bins(self, histogramdd):
+        arg = np.asarray([self.datax, self.datay]).T
+        kw = dict(bins=[20, 22], range=((0, 1), (0, 2)), weights=self.weights)
+        h0, e0 = histogramdd(arg, shape=0, **kw)
+        h1, e1 = np.histogramdd(arg, **kw)
+        assert np.all(np.isclose(h0, h1))
+        arg = (self.datax, self.datay, self.dataz)
+        h0, e0 = histogramdd(arg, bins=27, range=((0, 1), (0, 2), (0, 3)), shape=0, weights=self.weights)
+        h1, e1 = np.histogramdd(arg, bins=27, range=((0, 1), (0, 2), (0, 3)), weights=self.weights)
+        assert np.all(np.isclose(h0, h1)) and list(h0.shape) == [27, 27, 27]
+
+    def test_range_from_data_host_and_device(self, histogramdd):
+        import torch
+        h0, e0 = histogramdd((self.datax, self.datay), bins=(16, 16), shape=2, weights=self.weights)
+        assert e0[0][0] == self.datax.min() and e0[0][-1] == self.datax.max()
+        t = [torch.from_numpy(a).cuda() for a in (self.datax, self.datay)]
+        h1, e1 = histogramdd(t, bins=(16, 16), shape=2, weights=torch.from_numpy(self.weights).cuda())
+        assert all(np.array_equal(a, b) for a, b in zip(e0, e1))
+        assert np.allclose(h0, h1, rtol=1e-12, atol=1e-15)
+        h2, e2 = histogramdd((self.datax, self.datay), bins=(16, 16), range=((None, 0.9), None), shape=2)
+        assert e2[0][0] == self.datax.min() and e2[0][-1] == 0.9 and e2[1][-1] == self.datay.max()
+
+    def test_defaults_and_errors(self, histogramdd):
+        h, (e,) = histogramdd(self.datax, range=(0, 1))
+        assert h.shape == (800,)                          # default bins, default shape 2
+        h2, _ = histogramdd(self.datax, range=(0, 1), shape=None)
+        assert np.array_equal(h, h2)
+        with pytest.raises(TypeError):
+            histogramdd(self.datax, range=(0, 1), nonsense=1)
+        with pytest.raises(ValueError):
+            histogramdd((self.datax,) * 4, bins=4)
+
+
+class TestCreateField:
+    """test/test_particles.py:37-49 -- createField of p + p is twice createField of p."""
+
+    def _species(self, n=10000, device=None):
+        from postpic_b200 import ArraySource
+        rng = np.random.default_rng(0)
+        me, c = 9.109383e-31, 299792458.0
+        arrs = dict(x=rng.normal(0, 1, n), y=rng.normal(0, 1, n), z=rng.normal(0, 1, n),
+                    px=rng.normal(0, 1, n) ** 2 * me * c, py=rng.normal(0, 1, n) * me * c,
+                    pz=rng.normal(0, 1, n) * me * c, weight=1.0, mass=me, charge=-1.602176565e-19)
+        if device is not None:
+            import torch
+            arrs = {k: (torch.from_numpy(v).to(device) if isinstance(v, np.ndarray) else v) for k, v in arrs.items()}
+        return ArraySource('electron', arrs, extent={'x': (-4, 4), 'y': (-4, 4), 'z': (-4, 4)})
+
+    def test_linearity(self):
+        from postpic_b200 import MultiSpecies
+        p = MultiSpecies(self._species())
+        pp = p + p
+        f1 = p.createField('x', 'y', bins=[50, 40], simextent=True)
+        f2 = pp.createField('x', 'y', bins=[50, 40], simextent=True)
+        assert np.allclose(2 * f1.matrix, f2.matrix)
+        assert f1.matrix.shape == (50, 40) and f1.axes[0].name == 'x' and f1.axes[0].unit == 'm'
+
+    def test_energy_weighted_matches_numpy_formula_and_device(self, cf):
+        from postpic_b200 import MultiSpecies
+        src = self._species()
+        p = MultiSpecies(src)
+        kw = dict(weights='Ekin_MeV', bins=[64, 64], shape=3, rangex=(-3, 3), rangey=(-3, 3))
+        f = p.createField('x', 'y', **kw)
+        # independent evaluation of weight * Ekin_MeV and of the 1/dV normalisation
+        import scipy.constants as sc
+        a = src._arrays
+        np2 = (a['px'] ** 2 + a['py'] ** 2 + a['pz'] ** 2) / (a['mass'] * sc.c) ** 2
+        ekin = np2 / (np.sqrt(1 + np2) + 1) * a['mass'] * sc.c ** 2 / sc.elementary_charge / 1e6
+        h, ex, ey = cf.histogram2d(a['x'], a['y'], weights=ekin, range=((-3, 3), (-3, 3)), bins=(64, 64), shape=3)
+        dV = (ex[1] - ex[0]) * (ey[1] - ey[0])
+        assert np.allclose(f.matrix, h / dV, rtol=1e-11, atol=0)
+        assert f.name.startswith('Ekin_MeV')
+        pd = MultiSpecies(self._species(device='cuda'))
+        fd = pd.createField('x', 'y', **kw)
+        assert np.allclose(fd.matrix, f.matrix, rtol=1e-10, atol=1e-300)
+
+    def test_empty_and_aliases(self):
+        from postpic_b200 import MultiSpecies, ArraySource
+        empty = MultiSpecies(ArraySource('none', dict(x=np.empty(0), y=np.empty(0), weight=np.empty(0))))
+        h, edges = empty._createHistgram('x', 'y', bins=[5, 6], rangex=(0, 1))
+        assert h.shape == (5, 6) and not h.any() and np.array_equal(edges[1], np.linspace(0, 1, 7))
+        p = MultiSpecies(self._species())
+        h1, _ = p.createHistgram1d('x', bins=[32], rangex=(-3, 3))
+        h2, _ = p.createHistgram2d('x', 'y', bins=[8, 8], rangex=(-3, 3), rangey=(-3, 3))
+        h3, _ = p.createHistgram3d('x', 'y', 'z', bins=[4, 4, 4], rangex=(-3, 3), rangey=(-3, 3), rangez=(-3, 3))
+        assert h1.shape == (32,) and h2.shape == (8, 8) and h3.shape == (4, 4, 4)
+        with pytest.raises(TypeError):
+            p.createField('x', 'y', 'z', 'px')

@@ -1,0 +1,197 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header declares,
+the host-side set-up arithmetic, argument normalisation of histogramdd and the
+MultiSpecies dispatch (with the oracle standing in for the CUDA module -- allowed in
+tests/ only), and the no-fallback guarantee."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from postpic_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "ptg_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(ptg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 14
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.ptg_abi_version() == 1
+    assert lib.ptg_strerror(-4) == b"no usable sm_100 GPU"
+
+
+def test_library_contains_only_sm100a_code():
+    import shutil
+    import subprocess
+    from postpic_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_axis_setup_matches_reference_arithmetic():
+    from postpic_b200 import _lib
+    from postpic_b200._setup import axis_setup
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    cases_ = [(0.0, 1.0, 10), (0.001, 0.999, 1000), (-1.0, 1.0, 1024), (2.0, 2.0, 4), (0.0, 0.0, 3),
+              (1e-300, 1e-300, 5), (5.0, -5.0, 7), (0.0, 40e-6, 2048)]
+    cases_ += [(float(a), float(a + abs(b)), int(n)) for a, b, n in
+               zip(rng.normal(0, 10, 50), rng.normal(0, 3, 50), rng.integers(1, 5000, 50))]
+    for lo, hi, bins in cases_:
+        plo, pinv, edges = axis_setup((lo, hi), bins)
+        clo, chi, cinv = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        assert lib.ptg_axis_setup(lo, hi, bins, ctypes.byref(clo), ctypes.byref(chi), ctypes.byref(cinv)) == 0
+        assert clo.value == plo and cinv.value == pinv
+        assert edges[0] == plo and len(edges) == bins + 1
+        # the reference's expression, literally (pyx:53-60)
+        xmin, xmax = lo, hi
+        sx = np.spacing(xmax)
+        if np.abs(xmax - xmin) < sx:
+            xmax += sx
+            xmin -= sx
+        assert plo == xmin and np.array_equal(edges, np.linspace(xmin, xmax, bins + 1))
+        with np.errstate(over='ignore', divide='ignore'):
+            assert pinv == 1.0 / (xmax - xmin) * bins
+
+
+def test_shape_spellings():
+    from postpic_b200._setup import shape_order, shapes
+    assert shapes == [[0, 'NGP'], [1, 'tophat'], [2, 'triangle'], [3, 'spline3']]
+    for order, name in shapes:
+        assert shape_order(order) == order and shape_order(name) == order
+        assert shape_order(float(order)) == order and shape_order(np.int64(order)) == order
+    assert shape_order(True) == 1 and shape_order(False) == 0
+    for bad in (4, -1, 'cubic', None, 2.5):
+        with pytest.raises(ValueError):
+            shape_order(bad)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from postpic_b200 import _lib
+    from postpic_b200.particles import _particlestogrid as ptg
+    x = np.linspace(0.1, 0.9, 100)
+    with pytest.raises(_lib.NoDeviceError):
+        ptg.histogram(x, range=(0, 1), bins=10, shape=2)
+    with pytest.raises(_lib.NoDeviceError):
+        ptg.histogram2d(x, x, range=((0, 1), (0, 1)), bins=(4, 4), shape=0)
+    with pytest.raises(_lib.NoDeviceError):
+        _lib.device_info()
+    # argument errors are still reported before any device work
+    with pytest.raises(ValueError):
+        ptg.histogram2d(x, x[:5], range=((0, 1), (0, 1)), bins=(4, 4))
+    with pytest.raises(ValueError):
+        ptg.histogram(x, range=(0, 1), bins=4, shape=7)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "postpic_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "ptg_oracle" not in text, f
+
+
+@pytest.fixture
+def cpu_stack(monkeypatch, oracle):
+    """The Python host stack with the oracle in place of the CUDA module."""
+    from postpic_b200.particles import _routines
+    monkeypatch.setattr(_routines, "ptg", oracle)
+    return _routines
+
+
+def test_histogramdd_argument_forms(cpu_stack, oracle):
+    hdd = cpu_stack.histogramdd
+    rng = np.random.default_rng(3)
+    x, y, z, w = rng.random(1000), 2 * rng.random(1000), 3 * rng.random(1000), rng.random(1000)
+    h0, (e0,) = hdd(x, bins=20, range=(0, 1), shape=0)
+    for h, (e,) in [hdd((x,), bins=20, range=((0, 1),), shape=0), hdd((x,), bins=20, range=(0, 1), shape=0),
+                    hdd(x, bins=20, range=((0, 1),), shape=0), hdd(x, bins=(20,), range=((0, 1),), shape=0)]:
+        assert np.array_equal(h, h0) and np.array_equal(e, e0)
+    assert np.array_equal(h0, np.histogram(x, bins=20, range=(0, 1))[0])
+    # (N, D) array form == tuple form; default shape is 2; shape=None means default
+    nd = np.asarray([x, y]).T
+    a, ea = hdd(nd, bins=[20, 22], range=((0, 1), (0, 2)), weights=w)
+    b, eb = hdd((x, y), bins=[20, 22], range=((0, 1), (0, 2)), weights=w, shape=None)
+    c = oracle.histogram2d(x, y, weights=w, range=((0, 1), (0, 2)), bins=(20, 22), shape=2)[0]
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    # default bins, scalar bins, range completion from the data
+    assert hdd(x, range=(0, 1))[0].shape == (800,)
+    assert hdd((x, y), range=((0, 1), (0, 2)))[0].shape == (500, 500)
+    assert hdd((x, y, z), bins=27, range=((0, 1), (0, 2), (0, 3)), shape=0)[0].shape == (27, 27, 27)
+    h, (ex, ey) = hdd((x, y), bins=(8, 8), range=((None, 0.9), None))
+    assert ex[0] == x.min() and ex[-1] == 0.9 and ey[0] == y.min() and ey[-1] == y.max()
+    # lists are converted, ints are cast
+    assert np.array_equal(hdd(list(x), bins=20, range=(0, 1), shape=0)[0], h0)
+    assert hdd(np.arange(10), bins=5, range=(0, 10), shape=0)[0].sum() == 9
+    with pytest.raises(TypeError):
+        hdd(x, range=(0, 1), foo=3)
+    with pytest.raises(ValueError):
+        hdd((x, x, x, x), bins=3)
+    with pytest.raises(ValueError):
+        hdd((x, y), bins=4, range=(((0, 1), 1), (0, 1)))     # malformed range: non-scalar end
+
+
+def test_multispecies_dispatch_on_cpu_stack(cpu_stack, monkeypatch, oracle):
+    from postpic_b200.particles import particles as P
+    monkeypatch.setattr(P, "histogramdd", cpu_stack.histogramdd)
+    rng = np.random.default_rng(0)
+    n = 5000
+    me, c = 9.109383e-31, 299792458.0
+    src = P.ArraySource('electron', dict(x=rng.normal(0, 1, n), y=rng.normal(0, 1, n), z=rng.normal(0, 1, n),
+                                         px=rng.normal(0, 1, n) * me * c, py=rng.normal(0, 1, n) * me * c,
+                                         pz=rng.normal(0, 1, n) * me * c, weight=2.0, mass=me),
+                        extent={'x': (-4, 4), 'y': (-4, 4)})
+    p = P.MultiSpecies(src)
+    f1 = p.createField('x', 'y', bins=[50, 40], simextent=True)
+    f2 = (p + p).createField('x', 'y', bins=[50, 40], simextent=True)
+    assert np.allclose(2 * f1.matrix, f2.matrix)                    # test/test_particles.py:37-49
+    # 1/dV normalisation, weight * (expr), default shape 2
+    h, ex, ey = oracle.histogram2d(src.atomic('x'), src.atomic('y'), weights=np.full(n, 2.0),
+                                   range=((-4, 4), (-4, 4)), bins=(50, 40), shape=2)
+    assert np.allclose(f1.matrix, h / ((ex[1] - ex[0]) * (ey[1] - ey[0])), rtol=1e-14)
+    assert f1.axes[0].name == 'x' and f1.axes[1].unit == 'm' and f1.infostring == '5000 npart in 1 species'
+    # energy weights
+    import scipy.constants as sc
+    f3 = p.createField('x', weights='Ekin_MeV', bins=[32], rangex=(-3, 3), shape=3)
+    a = src._arrays
+    np2 = (a['px'] ** 2 + a['py'] ** 2 + a['pz'] ** 2) / (me * sc.c) ** 2
+    ek = 2.0 * (np2 / (np.sqrt(1 + np2) + 1) * me * sc.c ** 2 / sc.elementary_charge / 1e6)
+    h, e = oracle.histogram(a['x'], weights=ek, range=(-3, 3), bins=32, shape=3)
+    assert np.allclose(f3.matrix, h / (e[1] - e[0]), rtol=1e-12)
+    assert f3.name == 'Ekin_MeVelectron'
+    # simgrid is a no-op for bins (the reference's simgridpoints returns None)
+    assert p.createField('x', 'y', bins=[7, 9], simgrid=True).matrix.shape == (7, 9)
+    with pytest.raises(TypeError):
+        p.createField('x', bogus=1)
+    with pytest.raises(KeyError):
+        p.createField('nonexistent_scalar', bins=[4], rangex=(0, 1))
+    h, edges = p._createHistgram('nonexistent_scalar', bins=[4], rangex=(0, 1), force=True)
+    assert h.shape == (4,) and not h.any()
+
+
+def test_shard_bounds_cover_everything():
+    from postpic_b200.parallel import shard_bounds
+    for n in (0, 1, 7, 8, 1000003):
+        for ws in (1, 2, 3, 8):
+            spans = [shard_bounds(n, ws, r) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
