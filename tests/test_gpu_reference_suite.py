@@ -146,7 +146,7 @@ class TestHistogramdd:
         h, (e,) = histogramdd(self.datax, range=(0, 1))
         assert h.shape == (800,)                          # default bins, default shape 2
         h2, _ = histogramdd(self.datax, range=(0, 1), shape=None)
-        assert np.array_equal(h, h2)
+        assert np.allclose(h, h2, rtol=1e-13, atol=0)
         with pytest.raises(TypeError):
             histogramdd(self.datax, range=(0, 1), nonsense=1)
         with pytest.raises(ValueError):
