@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 #include "../../include/ptg_b200.h"
@@ -48,6 +49,9 @@ struct DeviceState {
     int64_t grid_cells = 0;
     double *scratch2 = nullptr;                   // 2 doubles for min/max
     bool staged = false;
+    // ring of probe verdicts for the TILED / AUTO methods (one entry per call in flight)
+    ptg::TileConfig *cfg_ring = nullptr;
+    std::atomic<unsigned> cfg_next{0};
 };
 
 DeviceState g_dev[kMaxDevices];
@@ -120,11 +124,21 @@ void fill_params(ptg::DepositParams &P, int ndim, int shape, int64_t n, const do
     P.grid = grid;
 }
 
-int pick_method(unsigned flags, int ndim, int shape) {
-    (void)ndim;
-    unsigned m = flags & PTG_METHOD_MASK;
-    if (m == PTG_METHOD_AUTO) m = shape == 0 ? PTG_METHOD_GLOBAL : PTG_METHOD_ROWS;
-    return (int)m;
+constexpr unsigned kCfgRing = 256;
+
+std::mutex g_ring_mu;     // never held together with g_mu by the same call path in reverse order
+
+int next_tile_config(DeviceState *d, ptg::TileConfig **out) {
+    if (!d->cfg_ring) {
+        std::lock_guard<std::mutex> lk(g_ring_mu);
+        if (!d->cfg_ring) {
+            ptg::TileConfig *ring = nullptr;
+            PTG_CUDA(cudaMalloc(&ring, kCfgRing * sizeof(ptg::TileConfig)));
+            d->cfg_ring = ring;
+        }
+    }
+    *out = d->cfg_ring + (d->cfg_next.fetch_add(1) % kCfgRing);
+    return PTG_OK;
 }
 
 int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double *x, const double *y,
@@ -134,14 +148,27 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
     fill_params(P, ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid);
     if (flags & PTG_ZERO_GRID)
         PTG_CUDA(cudaMemsetAsync(grid, 0, (size_t)ptg_padded_cells(ndim, shape, bins) * sizeof(double), st));
-    const int method = pick_method(flags, ndim, shape);
+    const unsigned method = flags & PTG_METHOD_MASK;
     switch (method) {
         case PTG_METHOD_GLOBAL:
-            PTG_CUDA(ptg::deposit_global(ndim, shape, P, false, d->sm_count, st));
+            PTG_CUDA(ptg::deposit_global(ndim, shape, P, false, nullptr, d->sm_count, st));
             break;
         case PTG_METHOD_ROWS:
-            PTG_CUDA(ptg::deposit_global(ndim, shape, P, shape > 0, d->sm_count, st));
+            PTG_CUDA(ptg::deposit_global(ndim, shape, P, shape > 0, nullptr, d->sm_count, st));
             break;
+        case PTG_METHOD_TILED:
+        case PTG_METHOD_AUTO: {
+            // probe -> (tiled kernel | rows kernel): both are launched, the probe's verdict in device
+            // memory decides which one returns immediately; no host round trip.
+            if (n <= 0) break;
+            ptg::TileConfig *cfg;
+            int rc = next_tile_config(d, &cfg);
+            if (rc) return rc;
+            const bool force = method == PTG_METHOD_TILED;
+            PTG_CUDA(ptg::deposit_tiled(ndim, shape, P, cfg, force, d->sm_count, st));
+            if (!force) PTG_CUDA(ptg::deposit_global(ndim, shape, P, shape > 0, cfg, d->sm_count, st));
+            break;
+        }
         default:
             return fail(PTG_EUNSUPPORTED, "deposition method 0x%x is not available in this build", method);
     }
@@ -398,7 +425,7 @@ int ptg_release(void) {
     if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); return PTG_OK; }
     for (int dev = 0; dev < kMaxDevices; ++dev) {
         DeviceState &d = g_dev[dev];
-        if (!d.staged && !d.grid) continue;
+        if (!d.staged && !d.grid && !d.cfg_ring) continue;
         cudaSetDevice(dev);
         for (int k = 0; k < kSlots; ++k) {
             if (d.slot[k]) cudaFree(d.slot[k]);
@@ -408,6 +435,8 @@ int ptg_release(void) {
         }
         if (d.grid) cudaFree(d.grid);
         if (d.scratch2) cudaFree(d.scratch2);
+        if (d.cfg_ring) cudaFree(d.cfg_ring);
+        d.cfg_ring = nullptr;
         d.grid = nullptr; d.scratch2 = nullptr; d.grid_cells = 0; d.staged = false;
     }
     cudaSetDevice(prev);

@@ -79,7 +79,8 @@ __device__ __forceinline__ void deposit_particle_global(const DepositParams &P, 
 }
 
 template <int ND, int S, bool W>
-__global__ void __launch_bounds__(kThreads) k_deposit_global(const DepositParams P) {
+__global__ void __launch_bounds__(kThreads) k_deposit_global(const DepositParams P, const TileConfig *gate) {
+    if (gate != nullptr && gate->useful) return;
     const int64_t nthreads = (int64_t)gridDim.x * kThreads;
     int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
@@ -128,7 +129,8 @@ template <int ND, int S> struct RowsCfg {
 };
 
 template <int ND, int S, bool W>
-__global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P) {
+__global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P, const TileConfig *gate) {
+    if (gate != nullptr && gate->useful) return;
     using C = RowsCfg<ND, S>;
     constexpr int NW = C::NW;
     __shared__ __align__(16) double stage_all[(kThreads / 32) * 32 * C::PS];
@@ -209,54 +211,54 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
 // launchers
 // ---------------------------------------------------------------------------------
 template <int ND, int S, bool W>
-static cudaError_t launch_global(const DepositParams &P, int sm_count, cudaStream_t st) {
+static cudaError_t launch_global(const DepositParams &P, const TileConfig *gate, int sm_count, cudaStream_t st) {
     if (P.n <= 0) return cudaSuccess;
     int64_t want = (P.n + (int64_t)kThreads * kUnroll - 1) / ((int64_t)kThreads * kUnroll);
     int64_t cap = (int64_t)sm_count * 8;                  // 8 x 256 threads = full occupancy
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
-    k_deposit_global<ND, S, W><<<blocks, kThreads, 0, st>>>(P);
+    k_deposit_global<ND, S, W><<<blocks, kThreads, 0, st>>>(P, gate);
     return cudaGetLastError();
 }
 
 template <int ND, int S, bool W>
-static cudaError_t launch_rows(const DepositParams &P, int sm_count, cudaStream_t st) {
+static cudaError_t launch_rows(const DepositParams &P, const TileConfig *gate, int sm_count, cudaStream_t st) {
     if (P.n <= 0) return cudaSuccess;
     int64_t want = (P.n + kThreads - 1) / kThreads;
     int64_t cap = (int64_t)sm_count * 8;
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
-    k_deposit_rows<ND, S, W><<<blocks, kThreads, 0, st>>>(P);
+    k_deposit_rows<ND, S, W><<<blocks, kThreads, 0, st>>>(P, gate);
     return cudaGetLastError();
 }
 
 template <int ND, int S>
-static cudaError_t dispatch_w(const DepositParams &P, bool rows, int sm_count, cudaStream_t st) {
+static cudaError_t dispatch_w(const DepositParams &P, bool rows, const TileConfig *gate, int sm_count, cudaStream_t st) {
     const bool weighted = P.p[3] != nullptr;
     if (rows) {
         if constexpr (S >= 1) {
-            return weighted ? launch_rows<ND, S, true>(P, sm_count, st) : launch_rows<ND, S, false>(P, sm_count, st);
+            return weighted ? launch_rows<ND, S, true>(P, gate, sm_count, st) : launch_rows<ND, S, false>(P, gate, sm_count, st);
         }
     }
-    return weighted ? launch_global<ND, S, true>(P, sm_count, st) : launch_global<ND, S, false>(P, sm_count, st);
+    return weighted ? launch_global<ND, S, true>(P, gate, sm_count, st) : launch_global<ND, S, false>(P, gate, sm_count, st);
 }
 
 template <int ND>
-static cudaError_t dispatch_s(int shape, const DepositParams &P, bool rows, int sm_count, cudaStream_t st) {
+static cudaError_t dispatch_s(int shape, const DepositParams &P, bool rows, const TileConfig *gate, int sm_count, cudaStream_t st) {
     switch (shape) {
-        case 0: return dispatch_w<ND, 0>(P, false, sm_count, st);
-        case 1: return dispatch_w<ND, 1>(P, rows, sm_count, st);
-        case 2: return dispatch_w<ND, 2>(P, rows, sm_count, st);
-        default: return dispatch_w<ND, 3>(P, rows, sm_count, st);
+        case 0: return dispatch_w<ND, 0>(P, false, gate, sm_count, st);
+        case 1: return dispatch_w<ND, 1>(P, rows, gate, sm_count, st);
+        case 2: return dispatch_w<ND, 2>(P, rows, gate, sm_count, st);
+        default: return dispatch_w<ND, 3>(P, rows, gate, sm_count, st);
     }
 }
 
-cudaError_t deposit_global(int ndim, int shape, const DepositParams &P, bool rows, int sm_count,
-                           cudaStream_t st) {
+cudaError_t deposit_global(int ndim, int shape, const DepositParams &P, bool rows, const TileConfig *gate,
+                           int sm_count, cudaStream_t st) {
     switch (ndim) {
-        case 1: return dispatch_s<1>(shape, P, rows, sm_count, st);
-        case 2: return dispatch_s<2>(shape, P, rows, sm_count, st);
-        default: return dispatch_s<3>(shape, P, rows, sm_count, st);
+        case 1: return dispatch_s<1>(shape, P, rows, gate, sm_count, st);
+        case 2: return dispatch_s<2>(shape, P, rows, gate, sm_count, st);
+        default: return dispatch_s<3>(shape, P, rows, gate, sm_count, st);
     }
 }
 

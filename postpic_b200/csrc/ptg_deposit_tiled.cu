@@ -1,0 +1,404 @@
+// ptg_deposit_tiled.cu -- method TILED: shared-memory privatised sub-grid tiles.
+//
+// One persistent CTA per SM walks a contiguous span of the particle arrays and keeps a
+// window ("tile") of the ghost-padded grid in its 200 KB of shared memory:
+//   * particles whose whole stencil falls inside the window are accumulated there
+//     with shared-memory atomics; runs of adjacent lanes that hit the same base cell
+//     (cell-ordered PIC output, tight bunches) are first summed across the warp with
+//     shuffles so that one lane commits the run (warp-aggregated atomics);
+//   * particles outside the window go straight to the grid in HBM/L2 with RED.F64,
+//     so the result is correct for any input -- the window only decides the speed;
+//   * the CTA watches its hit rate and, when most particles miss, merges the tile
+//     into the global grid and re-centres the window on the particles it is
+//     currently reading; at the end of its span the tile is merged once more.
+// The window *shape* is chosen per launch by a one-CTA probe kernel that looks at 16
+// blocks of 1024 consecutive particles: extents ~ 4 x the mean absolute deviation of
+// the stencil base cell inside a block, scaled to the tile budget.  For inputs without
+// locality (i.i.d. positions over a grid much larger than the tile) the probe marks
+// the tile as useless and the launcher's second kernel (method ROWS) does the work.
+//
+// Replaces the loops of /root/reference/postpic/particles/_particlestogrid.pyx
+// :70-129 (1-D), :181-276 (2-D), :341-463 (3-D).
+#include "ptg_internal.cuh"
+
+namespace ptg {
+
+constexpr int kTT = 512;                  // threads per CTA, one CTA per SM (<= 128 registers each)
+constexpr int kTileCells = 25600;         // 200 KB of doubles
+constexpr int kProbeBlocks = 16;
+constexpr int kEvalEvery = 4;             // sub-chunks between hit-rate evaluations
+
+// ---------------------------------------------------------------------------------
+// block-wide sum of a long long (all threads get the result)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ long long block_sum(long long v, long long *scratch /* >= 33 */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        long long t = lane < (int)(blockDim.x >> 5) ? scratch[lane] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+// stencil base cell of one particle on every axis (no weights): shared by probe and kernel
+template <int ND, int S>
+__device__ __forceinline__ bool base_cells(const DepositParams &P, double x, double y, double z, int (&b)[3]) {
+    b[0] = b[1] = b[2] = 0;
+    if (S == 0) {
+        bool ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], b[0]);
+        if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
+        if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
+        return ok;
+    } else {
+        constexpr int SS = S == 0 ? 1 : S;
+        double w[SS + 1];
+        bool ok = shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b[0], w);
+        if (ND >= 2) ok = shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], b[1], w) && ok;
+        if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b[2], w) && ok;
+        return ok;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// probe: pick the window shape
+// ---------------------------------------------------------------------------------
+template <int ND, int S>
+__global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig *cfg, int force) {
+    __shared__ long long scratch[34];
+    constexpr int NW = StencilWidth<S>::value;
+    double mad_sum[3] = {0, 0, 0};
+    int blocks_used = 0;
+    if (P.n >= 2 * kTT) {
+        for (int blk = 0; blk < kProbeBlocks; ++blk) {
+            const int64_t start = (P.n - kTT) / (kProbeBlocks - 1) * blk;
+            const int64_t i = start + threadIdx.x;
+            const double x = ld_stream(P.p[0] + i * P.stride[0]);
+            const double y = ND >= 2 ? ld_stream(P.p[1] + i * P.stride[1]) : 0.0;
+            const double z = ND >= 3 ? ld_stream(P.p[2] + i * P.stride[2]) : 0.0;
+            int b[3];
+            const bool ok = base_cells<ND, S>(P, x, y, z, b);
+            const long long cnt = block_sum(ok ? 1 : 0, scratch);
+            if (cnt < 32) continue;
+            ++blocks_used;
+            for (int a = 0; a < ND; ++a) {
+                const long long sum = block_sum(ok ? b[a] : 0, scratch);
+                const long long mean = sum / cnt;
+                const long long dev = block_sum(ok ? llabs((long long)b[a] - mean) : 0, scratch);
+                mad_sum[a] += (double)dev / (double)cnt;
+            }
+        }
+    }
+    if (threadIdx.x != 0) return;
+    TileConfig c;
+    c.useful = 0;
+    c.est_hit = 0.f;
+    c.ext[0] = c.ext[1] = c.ext[2] = 1;
+    if (blocks_used > 0 || force) {
+        double need[3] = {1, 1, 1}, prod = 1;
+        for (int a = 0; a < ND; ++a) {
+            const double mad = blocks_used ? mad_sum[a] / blocks_used : P.dims[a];
+            need[a] = 4.0 * mad + NW + 3;
+            if (need[a] > P.dims[a]) need[a] = P.dims[a];
+            prod *= need[a];
+        }
+        double ext[3] = {need[0], need[1], need[2]};
+        if (prod > kTileCells) {
+            // shrink all axes by a common factor, never below the stencil width
+            const double f = pow((double)kTileCells / prod, 1.0 / ND);
+            for (int a = 0; a < ND; ++a) { ext[a] = floor(need[a] * f); if (ext[a] < NW + 1) ext[a] = NW + 1; }
+        }
+        for (int a = 0; a < ND; ++a) c.ext[a] = (int)ext[a] < P.dims[a] ? (int)ext[a] : P.dims[a];
+        // the last axis keeps an even extent when it is a true window (16-byte alignment of rows)
+        if (c.ext[ND - 1] < P.dims[ND - 1] && (c.ext[ND - 1] & 1)) c.ext[ND - 1] -= 1;
+        long long cells = 1;
+        for (int a = 0; a < ND; ++a) cells *= c.ext[a];
+        while (cells > kTileCells) {                       // rounding safety
+            int big = 0;
+            for (int a = 1; a < ND; ++a) if (c.ext[a] > c.ext[big]) big = a;
+            cells = cells / c.ext[big] * (c.ext[big] - 2);
+            c.ext[big] -= 2;
+        }
+        // spend what is left of the budget on the slowest axis (bands of whole rows)
+        const long long rest = cells / c.ext[0];
+        long long rows = kTileCells / rest;
+        if (rows > P.dims[0]) rows = P.dims[0];
+        if (rows > c.ext[0]) c.ext[0] = (int)rows;
+        double hit = 1;
+        for (int a = 0; a < ND; ++a) hit *= fmin(1.0, (double)c.ext[a] / need[a]);
+        c.est_hit = (float)hit;
+        c.useful = (hit >= 0.45 || force) ? 1 : 0;
+    }
+    *cfg = c;
+}
+
+// ---------------------------------------------------------------------------------
+// the tiled deposit kernel
+// ---------------------------------------------------------------------------------
+struct Window {
+    int o[3];      // origin (padded cell index of the first cell held)
+    int e[3];      // extent
+};
+
+template <int ND>
+__device__ __forceinline__ void flush_tile(double *tile, const Window &wd, const DepositParams &P, int cells) {
+    // merge the tile into the global grid (coalesced along the last axis) and clear it
+    for (int c = threadIdx.x; c < cells; c += kTT) {
+        const double v = tile[c];
+        if (v != 0.0) {
+            int64_t lin;
+            if (ND == 1) lin = wd.o[0] + c;
+            else if (ND == 2) {
+                const int ix = c / wd.e[1], iy = c - ix * wd.e[1];
+                lin = (int64_t)(wd.o[0] + ix) * P.dims[1] + wd.o[1] + iy;
+            } else {
+                const int plane = wd.e[1] * wd.e[2];
+                const int ix = c / plane, r = c - ix * plane;
+                const int iy = r / wd.e[2], iz = r - iy * wd.e[2];
+                lin = ((int64_t)(wd.o[0] + ix) * P.dims[1] + wd.o[1] + iy) * P.dims[2] + wd.o[2] + iz;
+            }
+            red_add(P.grid + lin, v);
+            tile[c] = 0.0;
+        }
+    }
+}
+
+template <int ND, int S, bool W>
+__global__ void __launch_bounds__(kTT, 1) k_deposit_tiled(const DepositParams P, const TileConfig *cfgp) {
+    extern __shared__ double tile[];
+    __shared__ long long scratch[34];
+    __shared__ Window s_win;
+    __shared__ unsigned s_acc, s_miss;
+    constexpr int NW = StencilWidth<S>::value;
+    constexpr int SS = S == 0 ? 1 : S;
+
+    const TileConfig cfg = *cfgp;
+    if (!cfg.useful) return;
+    int cells = 1;
+    for (int a = 0; a < ND; ++a) cells *= cfg.ext[a];
+
+    for (int c = threadIdx.x; c < cells; c += kTT) tile[c] = 0.0;
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 3; ++a) { s_win.e[a] = a < ND ? cfg.ext[a] : 1; s_win.o[a] = 0; }
+        // a window that covers the whole axis never needs to move; the others start "nowhere"
+        for (int a = 0; a < ND; ++a) if (cfg.ext[a] < P.dims[a]) s_win.o[a] = -(1 << 28);
+        s_acc = 0; s_miss = 0;
+    }
+    __syncthreads();
+    Window wd = s_win;
+
+    // contiguous span of this CTA, a multiple of the CTA width
+    int64_t per = (P.n + gridDim.x - 1) / gridDim.x;
+    per = (per + kTT - 1) / kTT * kTT;
+    const int64_t begin = (int64_t)blockIdx.x * per;
+    const int64_t end = begin + per < P.n ? begin + per : P.n;
+    const int lane = threadIdx.x & 31;
+    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
+    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2], sw = P.stride[3];
+
+    // software pipeline: the raw values of the next sub-chunk are in flight while this one is deposited
+    double nx = 0, ny = 0, nz = 0, nwt = 1.0;
+    {
+        const int64_t i = begin + threadIdx.x;
+        if (i < end) {
+            nx = ld_stream(px + i * sx);
+            if (ND >= 2) ny = ld_stream(py + i * sy);
+            if (ND >= 3) nz = ld_stream(pz + i * sz);
+            if (W) nwt = ld_stream(pw + i * sw);
+        }
+    }
+    int since_eval = kEvalEvery - 1;       // first evaluation right after the first sub-chunk
+    unsigned acc_w = 0, miss_w = 0;        // per-warp counters (lane 0), published at evaluation time
+    for (int64_t i0 = begin; i0 < end; i0 += kTT) {
+        const int64_t i = i0 + threadIdx.x;
+        const double x = nx, y = ny, z = nz, w = nwt;
+        {
+            const int64_t j = i + kTT;
+            if (j < end) {
+                nx = ld_stream(px + j * sx);
+                if (ND >= 2) ny = ld_stream(py + j * sy);
+                if (ND >= 3) nz = ld_stream(pz + j * sz);
+                if (W) nwt = ld_stream(pw + j * sw);
+            }
+        }
+        // ---- stencil in registers --------------------------------------------------
+        int b[3] = {0, 0, 0};
+        double wx[NW], wy[NW], wz[NW];
+        bool ok = i < end;
+        if (ok) {
+            if constexpr (S == 0) {
+                ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], b[0]);
+                if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
+                if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
+                wx[0] = wy[0] = wz[0] = 1.0;
+            } else {
+                double (&rx)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wx);
+                double (&ry)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wy);
+                double (&rz)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wz);
+                ok = shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b[0], rx);
+                if (ND >= 2) ok = shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], b[1], ry) && ok;
+                if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b[2], rz) && ok;
+            }
+        }
+        // value of stencil cell (a, c, d), reference operation order: ((wx*wy)*wz)*w
+        auto value = [&](int a, int c, int d) -> double {
+            if (S == 0) return W ? w : 1.0;
+            if (ND == 1) return W ? __dmul_rn(wx[a], w) : wx[a];
+            double t = __dmul_rn(wx[a], wy[c]);
+            if (ND == 3) t = __dmul_rn(t, wz[d]);
+            return W ? __dmul_rn(t, w) : t;
+        };
+        constexpr int NV = ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW;
+        // stencils of up to 16 cells are materialised so that runs can be summed across the warp;
+        // the big 3-D stencils (27, 64 cells) are evaluated on the fly and never aggregated
+        constexpr bool AGG = NV <= 16;
+        constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
+        double v[AGG ? NV : 1];
+        bool commit = ok;
+        if constexpr (AGG) {
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int d = 0; d < NDD; ++d) v[(a * NC + c) * NDD + d] = value(a, c, d);
+            // ---- warp aggregation of runs of equal base cells -------------------------
+            const int key = ok ? (ND == 1 ? b[0] : ND == 2 ? b[0] * P.dims[1] + b[1]
+                                                           : (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2])
+                               : -1 - lane;
+            const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+            const bool head = lane == 0 || prev != key;
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+            if (__popc(heads) <= 16) {         // warp-uniform: runs are long enough to pay for the shuffles
+                const unsigned above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
+                const int next_head = above ? __ffs(above) - 1 : 32;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const bool take = lane + dd < next_head;
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        const double o = __shfl_down_sync(0xffffffffu, v[k], dd);
+                        if (take) v[k] = __dadd_rn(v[k], o);
+                    }
+                }
+                commit = ok && head;
+            }
+        }
+        auto cellval = [&](int a, int c, int d) -> double {
+            if constexpr (AGG) return v[(a * NC + c) * NDD + d];
+            else return value(a, c, d);
+        };
+        // ---- deposit: tile if the stencil fits the window, else straight to the grid ----
+        bool hit = commit;
+#pragma unroll
+        for (int a = 0; a < ND; ++a) hit = hit && b[a] >= wd.o[a] && b[a] + NW <= wd.o[a] + wd.e[a];
+        if (hit) {
+            const int p1 = ND >= 2 ? wd.e[1] : 1, p2 = ND >= 3 ? wd.e[2] : 1;
+            double *t = tile + ((b[0] - wd.o[0]) * p1 + (ND >= 2 ? b[1] - wd.o[1] : 0)) * p2 + (ND >= 3 ? b[2] - wd.o[2] : 0);
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int d = 0; d < NDD; ++d) atomicAdd(t + (a * p1 + c) * p2 + d, cellval(a, c, d));
+        } else if (commit) {
+            const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
+            double *g = P.grid + ((int64_t)b[0] * g1 + b[1]) * g2 + b[2];
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int d = 0; d < NDD; ++d) red_add(g + (a * g1 + c) * g2 + d, cellval(a, c, d));
+        }
+        // ---- hit-rate bookkeeping and window moves -------------------------------------
+        const unsigned m_ok = __ballot_sync(0xffffffffu, ok);
+        unsigned inside = ok;
+#pragma unroll
+        for (int a = 0; a < ND; ++a) inside = inside && b[a] >= wd.o[a] && b[a] + NW <= wd.o[a] + wd.e[a];
+        const unsigned m_in = __ballot_sync(0xffffffffu, inside);
+        acc_w += __popc(m_ok);
+        miss_w += __popc(m_ok & ~m_in);
+        if (++since_eval == kEvalEvery && i0 + kTT < end) {
+            since_eval = 0;
+            if (threadIdx.x == 0) { s_acc = 0; s_miss = 0; }
+            __syncthreads();
+            if (lane == 0 && acc_w) { atomicAdd(&s_acc, acc_w); atomicAdd(&s_miss, miss_w); }
+            acc_w = 0; miss_w = 0;
+            __syncthreads();
+            const unsigned acc = s_acc, miss = s_miss;
+            const bool move = acc >= 64 && miss * 2 > acc;
+            __syncthreads();
+            if (move) {
+                flush_tile<ND>(tile, wd, P, cells);
+                // new centre: mean base cell of the sub-chunk in registers
+                const long long cnt = block_sum(ok ? 1 : 0, scratch);
+                long long mean[3] = {0, 0, 0};
+                for (int a = 0; a < ND; ++a) mean[a] = block_sum(ok ? b[a] : 0, scratch) / (cnt > 0 ? cnt : 1);
+                if (threadIdx.x == 0) {
+                    for (int a = 0; a < ND; ++a) {
+                        if (wd.e[a] >= P.dims[a]) { s_win.o[a] = 0; continue; }
+                        long long o = mean[a] + NW / 2 - wd.e[a] / 2;
+                        if (a == ND - 1) o &= ~1ll;
+                        if (o < 0) o = 0;
+                        if (o > P.dims[a] - wd.e[a]) o = P.dims[a] - wd.e[a];
+                        s_win.o[a] = (int)o;
+                    }
+                }
+                __syncthreads();
+                wd = s_win;
+            }
+        }
+    }
+    __syncthreads();
+    flush_tile<ND>(tile, wd, P, cells);
+}
+
+// ---------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------
+template <int ND, int S, bool W>
+static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int force, int sm_count, cudaStream_t st) {
+    auto kern = k_deposit_tiled<ND, S, W>;
+    const size_t smem = (size_t)kTileCells * sizeof(double);
+    // per-device attribute, cheap to set: done on every launch so that any device works
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_probe<ND, S><<<1, kTT, 0, st>>>(P, cfg, force);
+    kern<<<sm_count, kTT, smem, st>>>(P, cfg);
+    return cudaGetLastError();
+}
+
+template <int ND, int S>
+static cudaError_t tiled_w(const DepositParams &P, TileConfig *cfg, int force, int sm, cudaStream_t st) {
+    return P.p[3] ? launch_tiled<ND, S, true>(P, cfg, force, sm, st) : launch_tiled<ND, S, false>(P, cfg, force, sm, st);
+}
+
+template <int ND>
+static cudaError_t tiled_s(int shape, const DepositParams &P, TileConfig *cfg, int force, int sm, cudaStream_t st) {
+    switch (shape) {
+        case 0: return tiled_w<ND, 0>(P, cfg, force, sm, st);
+        case 1: return tiled_w<ND, 1>(P, cfg, force, sm, st);
+        case 2: return tiled_w<ND, 2>(P, cfg, force, sm, st);
+        default: return tiled_w<ND, 3>(P, cfg, force, sm, st);
+    }
+}
+
+cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, int sm_count,
+                          cudaStream_t st) {
+    if (P.n <= 0) return cudaSuccess;
+    switch (ndim) {
+        case 1: return tiled_s<1>(shape, P, cfg, force, sm_count, st);
+        case 2: return tiled_s<2>(shape, P, cfg, force, sm_count, st);
+        default: return tiled_s<3>(shape, P, cfg, force, sm_count, st);
+    }
+}
+
+}  // namespace ptg

@@ -7,9 +7,23 @@
 
 namespace ptg {
 
-// ptg_deposit_global.cu
-cudaError_t deposit_global(int ndim, int shape, const DepositParams &P, bool rows, int sm_count,
-                           cudaStream_t st);
+// Decision record of the probe kernel (device memory): whether a shared-memory tile pays off
+// for this launch and the window extents it chose.
+struct TileConfig {
+    int useful;
+    int ext[3];
+    float est_hit;
+    int pad[3];
+};
+
+// ptg_deposit_global.cu -- `gate` (nullable): the kernels return at once when gate->useful != 0,
+// i.e. when the tiled kernel launched next to them is doing the work.
+cudaError_t deposit_global(int ndim, int shape, const DepositParams &P, bool rows, const TileConfig *gate,
+                           int sm_count, cudaStream_t st);
+
+// ptg_deposit_tiled.cu -- probe + tiled kernel; `force` ignores the probe's verdict
+cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, int sm_count,
+                          cudaStream_t st);
 
 // ptg_util.cu
 cudaError_t minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, int sm_count,

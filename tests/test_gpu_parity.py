@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "ptg_golden.npz"))
 ALL = [(nd, s, w) for nd in (1, 2, 3) for s in (0, 1, 2, 3) for w in (False, True)]
-METHODS = [None, 'global', 'rows']
+METHODS = [None, 'global', 'rows', 'tiled']
 
 
 @pytest.fixture(scope="module")
@@ -316,5 +316,16 @@ def test_large_properties_on_device(shape):
     # methods agree
     if shape:
         ga, _ = device.deposit([x, y], w, method='global', **kw)
-        gb, _ = device.deposit([x, y], w, method='rows', **kw)
-        assert float((ga - gb).abs().max()) <= 1e-12 * float(grid.abs().max())
+        for m in ('rows', 'tiled'):
+            gb, _ = device.deposit([x, y], w, method=m, **kw)
+            assert float((ga - gb).abs().max()) <= 1e-12 * float(grid.abs().max())
+        # x-sorted and cell-sorted orders exercise the tile window moves and the warp aggregation
+        order = torch.argsort(x)
+        gs, _ = device.deposit([x[order], y[order]], w[order], method='tiled', **kw)
+        assert float((gs - grid).abs().max()) <= 1e-12 * float(grid.abs().max())
+        cell = (x * 1024).floor() * 1024 + ((y + 1) * 512).floor()
+        order = torch.argsort(cell)
+        gc, _ = device.deposit([x[order], y[order]], w[order], method='tiled', **kw)
+        assert float((gc - grid).abs().max()) <= 1e-12 * float(grid.abs().max())
+        gc, _ = device.deposit([x[order], y[order]], w[order], method=None, **kw)
+        assert float((gc - grid).abs().max()) <= 1e-12 * float(grid.abs().max())
