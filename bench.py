@@ -56,7 +56,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--order", default="random", choices=["random", "sorted"])
+    ap.add_argument("--order", default="random", choices=["random", "sorted", "cellsorted"])
     ap.add_argument("--method", default="auto")
     ap.add_argument("--n", type=float, default=None, help="particles per GPU (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -92,6 +92,17 @@ def make_cloud_device(name, n, seed, order, device):
         del p2
     else:
         w = torch.rand(n, dtype=torch.float64, device=device, generator=g)
+    if order == "cellsorted":
+        # cell-ordered, as PIC codes that sort their particles by cell write them
+        key = torch.zeros(n, dtype=torch.int64, device=device)
+        for a in range(nd):
+            lo, hi = ranges[a]
+            key = key * bins[a] + ((coords[a] - lo) / (hi - lo) * bins[a]).floor().clamp_(0, bins[a] - 1).to(torch.int64)
+        idx = torch.argsort(key)
+        del key
+        coords = [c[idx].contiguous() for c in coords]
+        w = w[idx].contiguous()
+        del idx
     if order == "sorted":
         idx = torch.argsort(coords[0])
         coords = [c[idx].contiguous() for c in coords]

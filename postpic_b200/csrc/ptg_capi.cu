@@ -143,7 +143,8 @@ int next_tile_config(DeviceState *d, ptg::TileConfig **out) {
 
 int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double *x, const double *y,
                    const double *z, const double *w, const int64_t *strides, const double *lo,
-                   const double *inv, const int *bins, double *grid, unsigned flags, cudaStream_t st) {
+                   const double *inv, const int *bins, double *grid, unsigned flags, cudaStream_t st,
+                   void *workspace = nullptr, size_t workspace_bytes = 0) {
     ptg::DepositParams P;
     fill_params(P, ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid);
     if (flags & PTG_ZERO_GRID)
@@ -167,6 +168,25 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
             const bool force = method == PTG_METHOD_TILED;
             PTG_CUDA(ptg::deposit_tiled(ndim, shape, P, cfg, force, d->sm_count, st));
             if (!force) PTG_CUDA(ptg::deposit_global(ndim, shape, P, shape > 0, cfg, d->sm_count, st));
+            break;
+        }
+        case PTG_METHOD_SORTED: {
+            if (n <= 0) break;
+            if (n >= (int64_t(1) << 32)) return fail(PTG_EUNSUPPORTED, "method SORTED handles < 2^32 particles per call");
+            const size_t need = ptg::sorted_workspace_bytes(n, ptg_padded_cells(ndim, shape, bins));
+            if (workspace && workspace_bytes >= need) {
+                PTG_CUDA(ptg::deposit_sorted(ndim, shape, P, workspace, workspace_bytes, d->sm_count, st));
+            } else if (workspace) {
+                return fail(PTG_ENOMEM, "workspace of %zu bytes given, method SORTED needs %zu", workspace_bytes, need);
+            } else {
+                // no workspace supplied: stream-ordered allocation, released after the last kernel
+                void *ws = nullptr;
+                PTG_CUDA(cudaMallocAsync(&ws, need, st));
+                cudaError_t e = ptg::deposit_sorted(ndim, shape, P, ws, need, d->sm_count, st);
+                cudaError_t e2 = cudaFreeAsync(ws, st);
+                PTG_CUDA(e);
+                PTG_CUDA(e2);
+            }
             break;
         }
         default:
@@ -280,21 +300,22 @@ int64_t ptg_padded_cells(int ndim, int shape, const int *bins) {
 }
 
 size_t ptg_workspace_bytes(int ndim, int shape, int64_t n, const int *bins, unsigned flags) {
-    (void)ndim; (void)shape; (void)n; (void)bins; (void)flags;
-    return 0;
+    if ((flags & PTG_METHOD_MASK) != PTG_METHOD_SORTED || n <= 0) return 0;
+    const int64_t cells = ptg_padded_cells(ndim, shape, bins);
+    if (cells <= 0) return 0;
+    return ptg::sorted_workspace_bytes(n, cells);
 }
 
 int ptg_deposit_f64(int ndim, int shape, int64_t n, const double *x, const double *y, const double *z,
                     const double *w, const int64_t *strides, const double *lo, const double *inv,
                     const int *bins, double *grid, unsigned flags, void *workspace, size_t workspace_bytes,
                     void *stream) {
-    (void)workspace; (void)workspace_bytes;
     int rc = validate(ndim, shape, n, x, y, z, lo, inv, bins, grid);
     if (rc) return rc;
     DeviceState *d;
     if ((rc = current_device_state(&d))) return rc;
     return deposit_device(d, ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid, flags,
-                          (cudaStream_t)stream);
+                          (cudaStream_t)stream, workspace, workspace_bytes);
 }
 
 int ptg_minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, void *stream) {
@@ -348,10 +369,12 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
 
     const double *src[4] = {x, ndim >= 2 ? y : nullptr, ndim >= 3 ? z : nullptr, w};
     const unsigned dflags = flags & ~PTG_ZERO_GRID;
+    // the deterministic method must add the chunks to the grid in a fixed order: one stream
+    const bool ordered = (flags & PTG_METHOD_MASK) == PTG_METHOD_SORTED;
     int slot = 0;
     for (int64_t off = 0; off < n; off += kChunk, slot = (slot + 1) % kSlots) {
         const int64_t m = n - off < kChunk ? n - off : kChunk;
-        cudaStream_t st = d->stream[slot];
+        cudaStream_t st = ordered ? d->stream[0] : d->stream[slot];
         double *dptr[4] = {nullptr, nullptr, nullptr, nullptr};
         for (int k = 0; k < 4; ++k) {
             if (!src[k]) continue;

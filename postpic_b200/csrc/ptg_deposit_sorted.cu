@@ -1,0 +1,234 @@
+// ptg_deposit_sorted.cu -- method SORTED: deterministic deposition without atomics.
+//
+//   1. k_cell_keys      key[i] = padded linear index of particle i's stencil base cell
+//                       (rejected particles get the sentinel key `cells`)
+//   2. stable LSD radix sort of (key, particle index) pairs -- cub::DeviceRadixSort, the
+//      one library call on this path (NVIDIA's CUB ships inside the CUDA toolkit); only
+//      the bits a key can have are sorted
+//   3. k_cell_offsets   CSR offsets: particles of base cell c are idx[off[c] .. off[c+1])
+//                       in ORIGINAL particle order (the sort is stable)
+//   4. k_segment_reduce one launch per stencil "colour" (base cells with equal coordinates
+//      modulo the stencil width): stencils of one colour never overlap, so one warp per
+//      base cell sums its segment in registers (lane l takes particles l, l+32, ... in
+//      order, then a fixed xor-butterfly) and adds the (S+1)^ndim totals to the grid with
+//      plain loads and stores.  Colours run one after the other on the stream, so every
+//      grid cell receives its (S+1)^ndim contributions in a fixed order.
+// No floating-point atomic anywhere: the result is bit-reproducible from run to run
+// and independent of the hardware's scheduling; it is the variant for clustered inputs
+// where atomic contention is worst.  (It is NOT the reference's summation order -- that
+// one is strictly sequential -- so parity is within rounding, not bit-exact.)
+//
+// Replaces the loops of /root/reference/postpic/particles/_particlestogrid.pyx
+// :70-129 (1-D), :181-276 (2-D), :341-463 (3-D).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "ptg_internal.cuh"
+
+namespace ptg {
+
+template <int ND, int S>
+__global__ void __launch_bounds__(256) k_cell_keys(const DepositParams P, uint32_t cells, uint32_t *keys,
+                                                    uint32_t *idx) {
+    constexpr int SS = S == 0 ? 1 : S;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += step) {
+        const double x = ld_stream(P.p[0] + i * P.stride[0]);
+        const double y = ND >= 2 ? ld_stream(P.p[1] + i * P.stride[1]) : 0.0;
+        const double z = ND >= 3 ? ld_stream(P.p[2] + i * P.stride[2]) : 0.0;
+        int b[3] = {0, 0, 0};
+        bool ok;
+        if constexpr (S == 0) {
+            ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], b[0]);
+            if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
+            if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
+        } else {
+            double w[SS + 1];
+            ok = shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b[0], w);
+            if (ND >= 2) ok = shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], b[1], w) && ok;
+            if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b[2], w) && ok;
+        }
+        uint32_t key = cells;
+        if (ok) key = (uint32_t)((b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2]);    // dims beyond ndim are 1
+        keys[i] = key;
+        idx[i] = (uint32_t)i;
+    }
+}
+
+// off[c] = first position in the sorted key array whose key is >= c, for c in [0, cells]
+__global__ void __launch_bounds__(256) k_cell_offsets(const uint32_t *keys, int64_t n, uint32_t cells,
+                                                       uint32_t *off) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += step) {
+        const uint32_t lo = i == 0 ? 0u : keys[i - 1] + 1u;         // first key value that starts at >= i
+        const uint32_t hi = i == n ? cells : keys[i];
+        if (i == 0 || i == n || keys[i - 1] != hi)
+            for (uint32_t c = lo; c <= hi && c <= cells; ++c) off[c] = (uint32_t)i;
+    }
+}
+
+template <int ND, int S, bool W>
+__global__ void __launch_bounds__(256) k_segment_reduce(const DepositParams P, const uint32_t *idx,
+                                                         const uint32_t *off, int cx, int cy, int cz) {
+    constexpr int NW = StencilWidth<S>::value;
+    constexpr int SS = S == 0 ? 1 : S;
+    constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
+    constexpr int NV = NA * NC * NDD;
+    // base cells of this colour: b = colour + NW * k, with b + NW <= dims
+    const int nx = (P.dims[0] - NW - cx) / NW + 1;
+    const int ny = ND >= 2 ? (P.dims[1] - NW - cy) / NW + 1 : 1;
+    const int nz = ND >= 3 ? (P.dims[2] - NW - cz) / NW + 1 : 1;
+    if (nx <= 0 || ny <= 0 || nz <= 0) return;
+    const int64_t ncell = (int64_t)nx * ny * nz;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t cc = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); cc < ncell; cc += nwarps) {
+        const int kz = (int)(cc % nz), ky = (int)((cc / nz) % ny), kx = (int)(cc / ((int64_t)nz * ny));
+        const int bx = cx + NW * kx, by = cy + NW * ky, bz = cz + NW * kz;
+        const uint32_t lin = (uint32_t)((bx * P.dims[1] + by) * P.dims[2] + bz);
+        const uint32_t s0 = off[lin], s1 = off[lin + 1];
+        if (s0 == s1) continue;                                    // warp-uniform
+        double acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        for (uint32_t p = s0 + lane; p < s1; p += 32) {
+            const int64_t i = idx[p];
+            const double x = P.p[0][i * P.stride[0]];
+            const double y = ND >= 2 ? P.p[1][i * P.stride[1]] : 0.0;
+            const double z = ND >= 3 ? P.p[2][i * P.stride[2]] : 0.0;
+            const double w = W ? P.p[3][i * P.stride[3]] : 1.0;
+            double wx[NW], wy[NW], wz[NW];
+            int b0, b1, b2;
+            if constexpr (S == 0) {
+                wx[0] = wy[0] = wz[0] = 1.0;
+            } else {
+                double (&rx)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wx);
+                double (&ry)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wy);
+                double (&rz)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wz);
+                shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b0, rx);
+                if (ND >= 2) shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], b1, ry);
+                if (ND >= 3) shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b2, rz);
+            }
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int d = 0; d < NDD; ++d) {
+                        double v;
+                        if (S == 0) v = W ? w : 1.0;
+                        else if (ND == 1) v = W ? __dmul_rn(wx[a], w) : wx[a];
+                        else {
+                            v = __dmul_rn(wx[a], wy[c]);
+                            if (ND == 3) v = __dmul_rn(v, wz[d]);
+                            if (W) v = __dmul_rn(v, w);
+                        }
+                        acc[(a * NC + c) * NDD + d] = __dadd_rn(acc[(a * NC + c) * NDD + d], v);
+                    }
+        }
+        // fixed-order butterfly: every lane ends with the same total
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[k] = __dadd_rn(acc[k], __shfl_xor_sync(0xffffffffu, acc[k], o));
+        if (lane == 0) {
+            const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
+            double *g = P.grid + ((int64_t)bx * g1 + by) * g2 + bz;
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int d = 0; d < NDD; ++d) {
+                        double *q = g + (a * g1 + c) * g2 + d;
+                        *q = __dadd_rn(*q, acc[(a * NC + c) * NDD + d]);
+                    }
+        }
+    }
+}
+
+static int key_bits(uint32_t cells) {
+    int b = 1;
+    while (b < 32 && (cells >> b) != 0) ++b;
+    return b;
+}
+
+size_t sorted_workspace_bytes(int64_t n, int64_t cells) {
+    // 4 arrays of n u32 (double-buffered keys and indices), offsets, CUB scratch (bounded: with
+    // DoubleBuffer the onesweep scratch is histograms + look-back state, well under 16 MiB + n/64)
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    return 4 * al((size_t)n * 4) + al((size_t)(cells + 2) * 4) + al((size_t)16 << 20) + al((size_t)n / 16);
+}
+
+template <int ND, int S, bool W>
+static cudaError_t run_sorted(const DepositParams &P, void *ws, size_t ws_bytes, int sm_count, cudaStream_t st) {
+    const int64_t cells64 = (int64_t)P.dims[0] * P.dims[1] * P.dims[2];
+    const uint32_t cells = (uint32_t)cells64;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    char *base = static_cast<char *>(ws);
+    uint32_t *k0 = reinterpret_cast<uint32_t *>(base); base += al((size_t)P.n * 4);
+    uint32_t *k1 = reinterpret_cast<uint32_t *>(base); base += al((size_t)P.n * 4);
+    uint32_t *i0 = reinterpret_cast<uint32_t *>(base); base += al((size_t)P.n * 4);
+    uint32_t *i1 = reinterpret_cast<uint32_t *>(base); base += al((size_t)P.n * 4);
+    uint32_t *off = reinterpret_cast<uint32_t *>(base); base += al((size_t)(cells + 2) * 4);
+    void *cub_tmp = base;
+    size_t cub_avail = ws_bytes - (size_t)(base - static_cast<char *>(ws));
+
+    const int64_t cap = (int64_t)sm_count * 8;
+    int64_t want = (P.n + 256 * 4 - 1) / (256 * 4);
+    int blocks = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    k_cell_keys<ND, S><<<blocks, 256, 0, st>>>(P, cells, k0, i0);
+
+    cub::DoubleBuffer<uint32_t> dk(k0, k1), di(i0, i1);
+    size_t need = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, dk, di, P.n, 0, key_bits(cells), st);
+    if (e != cudaSuccess) return e;
+    if (need > cub_avail) return cudaErrorMemoryAllocation;
+    e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, dk, di, P.n, 0, key_bits(cells), st);
+    if (e != cudaSuccess) return e;
+
+    want = (P.n + 1 + 255) / 256;
+    blocks = (int)(want < cap ? want : cap);
+    k_cell_offsets<<<blocks, 256, 0, st>>>(dk.Current(), P.n, cells, off);
+
+    constexpr int NW = StencilWidth<S>::value;
+    const int ncx = NW, ncy = ND >= 2 ? NW : 1, ncz = ND >= 3 ? NW : 1;
+    for (int cx = 0; cx < ncx; ++cx)
+        for (int cy = 0; cy < ncy; ++cy)
+            for (int cz = 0; cz < ncz; ++cz) {
+                const int64_t ncell = ((int64_t)(P.dims[0] - NW - cx) / NW + 1) *
+                                      (ND >= 2 ? (P.dims[1] - NW - cy) / NW + 1 : 1) *
+                                      (ND >= 3 ? (P.dims[2] - NW - cz) / NW + 1 : 1);
+                if (ncell <= 0) continue;
+                int64_t wantb = (ncell + 7) / 8;                  // 8 warps per CTA
+                int nb = (int)(wantb < cap * 4 ? wantb : cap * 4);
+                k_segment_reduce<ND, S, W><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
+            }
+    return cudaGetLastError();
+}
+
+template <int ND, int S>
+static cudaError_t sorted_w(const DepositParams &P, void *ws, size_t wsb, int sm, cudaStream_t st) {
+    return P.p[3] ? run_sorted<ND, S, true>(P, ws, wsb, sm, st) : run_sorted<ND, S, false>(P, ws, wsb, sm, st);
+}
+
+template <int ND>
+static cudaError_t sorted_s(int shape, const DepositParams &P, void *ws, size_t wsb, int sm, cudaStream_t st) {
+    switch (shape) {
+        case 0: return sorted_w<ND, 0>(P, ws, wsb, sm, st);
+        case 1: return sorted_w<ND, 1>(P, ws, wsb, sm, st);
+        case 2: return sorted_w<ND, 2>(P, ws, wsb, sm, st);
+        default: return sorted_w<ND, 3>(P, ws, wsb, sm, st);
+    }
+}
+
+cudaError_t deposit_sorted(int ndim, int shape, const DepositParams &P, void *ws, size_t ws_bytes, int sm_count,
+                           cudaStream_t st) {
+    if (P.n <= 0) return cudaSuccess;
+    switch (ndim) {
+        case 1: return sorted_s<1>(shape, P, ws, ws_bytes, sm_count, st);
+        case 2: return sorted_s<2>(shape, P, ws, ws_bytes, sm_count, st);
+        default: return sorted_s<3>(shape, P, ws, ws_bytes, sm_count, st);
+    }
+}
+
+}  // namespace ptg

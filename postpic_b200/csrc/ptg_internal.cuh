@@ -25,6 +25,12 @@ cudaError_t deposit_global(int ndim, int shape, const DepositParams &P, bool row
 cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, int sm_count,
                           cudaStream_t st);
 
+// ptg_deposit_sorted.cu -- deterministic sort-by-cell + segmented reduce; needs a workspace of
+// sorted_workspace_bytes(n, cells) bytes
+size_t sorted_workspace_bytes(int64_t n, int64_t cells);
+cudaError_t deposit_sorted(int ndim, int shape, const DepositParams &P, void *ws, size_t ws_bytes, int sm_count,
+                           cudaStream_t st);
+
 // ptg_util.cu
 cudaError_t minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, int sm_count,
                        cudaStream_t st);

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "ptg_golden.npz"))
 ALL = [(nd, s, w) for nd in (1, 2, 3) for s in (0, 1, 2, 3) for w in (False, True)]
-METHODS = [None, 'global', 'rows', 'tiled']
+METHODS = [None, 'global', 'rows', 'tiled', 'sorted']
 
 
 @pytest.fixture(scope="module")
@@ -316,7 +316,7 @@ def test_large_properties_on_device(shape):
     # methods agree
     if shape:
         ga, _ = device.deposit([x, y], w, method='global', **kw)
-        for m in ('rows', 'tiled'):
+        for m in ('rows', 'tiled', 'sorted'):
             gb, _ = device.deposit([x, y], w, method=m, **kw)
             assert float((ga - gb).abs().max()) <= 1e-12 * float(grid.abs().max())
         # x-sorted and cell-sorted orders exercise the tile window moves and the warp aggregation
@@ -329,3 +329,27 @@ def test_large_properties_on_device(shape):
         assert float((gc - grid).abs().max()) <= 1e-12 * float(grid.abs().max())
         gc, _ = device.deposit([x[order], y[order]], w[order], method=None, **kw)
         assert float((gc - grid).abs().max()) <= 1e-12 * float(grid.abs().max())
+
+
+@pytest.mark.parametrize("nd,shape", [(1, 1), (2, 0), (2, 2), (2, 3), (3, 1), (3, 3)])
+def test_sorted_method_is_bit_reproducible(nd, shape):
+    """method 'sorted' (sort by cell + segmented reduce, no atomics): repeated runs are bitwise
+    identical, also on a clustered cloud where the atomic paths contend most."""
+    import torch
+    from postpic_b200 import device
+    n = 3_000_000
+    g = torch.Generator(device='cuda').manual_seed(5 + nd + shape)
+    coords = []
+    for a in range(nd):
+        u = torch.rand(n, dtype=torch.float64, device='cuda', generator=g)
+        pick = torch.rand(n, device='cuda', generator=g) < 0.9
+        coords.append(torch.where(pick, 0.45 + 0.1 * u, u * 1.1 - 0.05))
+    w = torch.rand(n, dtype=torch.float64, device='cuda', generator=g)
+    bins = [(4096,), (512, 384), (96, 80, 64)][nd - 1]
+    kw = dict(range=[(0, 1)] * nd, bins=bins, shape=shape)
+    g1, plan = device.deposit(coords, w, method='sorted', **kw)
+    g2, _ = device.deposit(coords, w, method='sorted', **kw)
+    g3, _ = device.deposit(coords, w, method='sorted', **kw)
+    assert torch.equal(g1, g2) and torch.equal(g1, g3)
+    ga, _ = device.deposit(coords, w, method='global', **kw)
+    assert float((g1 - ga).abs().max()) <= 1e-12 * float(ga.abs().max())
