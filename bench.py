@@ -364,11 +364,14 @@ def run_b200_arm(args):
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
     # parity spot-check of what was just timed (cheap: mass conservation incl. ghost cells)
-    total_w = float(w.sum())
+    tw = w.sum()
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.SUM)
+    total_w = float(tw)
     step()
     torch.cuda.synchronize()
     dep = float(grid.sum())
-    mass_err = abs(dep - total_w * world) / (total_w * world)
+    mass_err = abs(dep - total_w) / total_w
 
     # end to end through the public API with host (pinned) inputs
     e2e = None
@@ -420,7 +423,8 @@ def run_b200_arm(args):
                        "parallelism": "particles sharded over %d GPU(s), private grids, NCCL all-reduce" % world
                        if world > 1 else "1 GPU", "device": info["name"], "sm_count": info["sm_count"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": args.steps, "clocks": clocks.summary(),
+            "gpu_launches": args.steps * world * {"auto": 4, "tiled": 2}.get(args.method, 1),
+            "clocks": clocks.summary(),
             "parity": {"mass_conservation_rel_err": mass_err},
         }
         print(json.dumps(line))

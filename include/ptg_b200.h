@@ -55,7 +55,9 @@ extern "C" {
 
 /* ---- flags for the deposit entry points ------------------------------------------ */
 #define PTG_ZERO_GRID        0x1u   /* clear the padded grid before depositing                     */
-/* deposition method (bits 4..7); AUTO picks by grid size / dimensionality                       */
+/* deposition method (bits 4..7).  AUTO launches a one-CTA probe kernel that looks at 16 blocks of
+ * consecutive particles and lets exactly one of RUNS / TILED / ROWS do the work (decided on
+ * the device, no host round trip)                                                             */
 #define PTG_METHOD_MASK      0xF0u
 #define PTG_METHOD_AUTO      0x00u
 #define PTG_METHOD_GLOBAL    0x10u  /* one RED.E.ADD.F64 per stencil cell, straight to L2          */
@@ -64,6 +66,8 @@ extern "C" {
 #define PTG_METHOD_TILED     0x30u  /* shared-memory privatised sub-grid tile per CTA, warp-
                                        aggregated updates, tile merge to HBM                      */
 #define PTG_METHOD_SORTED    0x40u  /* deterministic: sort by cell + segmented reduce, no atomics  */
+#define PTG_METHOD_RUNS      0x50u  /* cell-ordered input: run-length accumulation in registers,
+                                       one reduction per run instead of one per particle          */
 
 /* ---- introspection ------------------------------------------------------------- */
 int         ptg_abi_version(void);

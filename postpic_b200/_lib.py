@@ -23,8 +23,9 @@ METHOD_GLOBAL = 0x10
 METHOD_ROWS = 0x20
 METHOD_TILED = 0x30
 METHOD_SORTED = 0x40
+METHOD_RUNS = 0x50
 METHODS = {None: METHOD_AUTO, 'auto': METHOD_AUTO, 'global': METHOD_GLOBAL, 'rows': METHOD_ROWS,
-           'tiled': METHOD_TILED, 'sorted': METHOD_SORTED}
+           'tiled': METHOD_TILED, 'sorted': METHOD_SORTED, 'runs': METHOD_RUNS}
 
 
 class PtgError(RuntimeError):

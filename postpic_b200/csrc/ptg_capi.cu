@@ -167,9 +167,15 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
             if (rc) return rc;
             const bool force = method == PTG_METHOD_TILED;
             PTG_CUDA(ptg::deposit_tiled(ndim, shape, P, cfg, force, d->sm_count, st));
-            if (!force) PTG_CUDA(ptg::deposit_global(ndim, shape, P, shape > 0, cfg, d->sm_count, st));
+            if (!force) {
+                PTG_CUDA(ptg::deposit_runs(ndim, shape, P, cfg, d->sm_count, st));
+                PTG_CUDA(ptg::deposit_global(ndim, shape, P, shape > 0, cfg, d->sm_count, st));
+            }
             break;
         }
+        case PTG_METHOD_RUNS:
+            PTG_CUDA(ptg::deposit_runs(ndim, shape, P, nullptr, d->sm_count, st));
+            break;
         case PTG_METHOD_SORTED: {
             if (n <= 0) break;
             if (n >= (int64_t(1) << 32)) return fail(PTG_EUNSUPPORTED, "method SORTED handles < 2^32 particles per call");

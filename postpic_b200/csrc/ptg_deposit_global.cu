@@ -80,7 +80,7 @@ __device__ __forceinline__ void deposit_particle_global(const DepositParams &P, 
 
 template <int ND, int S, bool W>
 __global__ void __launch_bounds__(kThreads) k_deposit_global(const DepositParams P, const TileConfig *gate) {
-    if (gate != nullptr && gate->useful) return;
+    if (gate != nullptr && gate->mode != kModeRows) return;
     const int64_t nthreads = (int64_t)gridDim.x * kThreads;
     int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
@@ -130,7 +130,7 @@ template <int ND, int S> struct RowsCfg {
 
 template <int ND, int S, bool W>
 __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P, const TileConfig *gate) {
-    if (gate != nullptr && gate->useful) return;
+    if (gate != nullptr && gate->mode != kModeRows) return;
     using C = RowsCfg<ND, S>;
     constexpr int NW = C::NW;
     __shared__ __align__(16) double stage_all[(kThreads / 32) * 32 * C::PS];

@@ -1,0 +1,202 @@
+// ptg_deposit_runs.cu -- method RUNS: run-length accumulation in registers.
+//
+// For cell-ordered input (PIC codes that sort their particles by cell write their dumps
+// that way; 1e8..1e9 particles on 1e6 cells means ~100..1000 consecutive particles per
+// cell) almost every particle lands on the same stencil as its predecessor.  Each thread
+// therefore walks K CONSECUTIVE particles, keeps the stencil sums of the current run in
+// registers and only commits when the base cell changes; the runs still open at the end
+// of the K particles are merged across the warp with a segmented shuffle reduction, and
+// one lane per run issues the (S+1)^ndim RED.F64.  Scatter traffic drops from
+// (S+1)^ndim reductions per particle to (S+1)^ndim per run, so the kernel is bound by
+// the streaming read of the particle arrays -- the HBM roofline -- instead of by the
+// L2 atomic units.  Input without runs is still deposited correctly, only slowly (one
+// uncoalesced RED per stencil cell per particle); AUTO selects this method only when
+// the probe kernel saw runs.
+//
+// Particle arrays are read with 16-byte vector loads when contiguous and aligned
+// (every lane reads K consecutive doubles = 2 sectors, a warp 32*K*8 contiguous bytes).
+//
+// Replaces the loops of /root/reference/postpic/particles/_particlestogrid.pyx
+// :70-129 (1-D), :181-276 (2-D), :341-463 (3-D).
+#include "ptg_internal.cuh"
+
+namespace ptg {
+
+constexpr int kRT = 256;      // threads per CTA
+constexpr int kRK = 4;        // consecutive particles per thread
+
+__device__ __forceinline__ void ld_stream_v2(const double *p, double &a, double &b) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+}
+
+// K consecutive values starting at element i (all K valid)
+template <bool VEC>
+__device__ __forceinline__ void load_k(const double *base, int64_t stride, int64_t i, double (&v)[kRK]) {
+    if (VEC) {
+#pragma unroll
+        for (int j = 0; j < kRK; j += 2) ld_stream_v2(base + i + j, v[j], v[j + 1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kRK; ++j) v[j] = __ldg(base + (i + j) * stride);   // L1 keeps the shared sectors
+    }
+}
+
+template <int ND, int S, bool W, bool VEC>
+__global__ void __launch_bounds__(kRT) k_deposit_runs(const DepositParams P, const TileConfig *gate) {
+    if (gate != nullptr && gate->mode != kModeRuns) return;
+    constexpr int NW = StencilWidth<S>::value;
+    constexpr int SS = S == 0 ? 1 : S;
+    constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
+    constexpr int NV = NA * NC * NDD;
+    const int lane = threadIdx.x & 31;
+    const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
+
+    auto commit = [&](int key, const double (&acc)[NV]) {
+        // key = padded linear index of the base cell
+        double *g = P.grid + key;
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                for (int d = 0; d < NDD; ++d) red_add(g + (a * g1 + c) * g2 + d, acc[(a * NC + c) * NDD + d]);
+    };
+
+    // contiguous span per CTA so that concurrently running CTAs work on different grid regions
+    const int64_t per_cta = ((P.n + gridDim.x - 1) / gridDim.x + kRT * kRK - 1) / (kRT * kRK) * (kRT * kRK);
+    const int64_t begin = (int64_t)blockIdx.x * per_cta;
+    const int64_t end = begin + per_cta < P.n ? begin + per_cta : P.n;
+
+    for (int64_t c0 = begin; c0 < end; c0 += kRT * kRK) {
+        const int64_t i0 = c0 + (int64_t)threadIdx.x * kRK;
+        double x[kRK], y[kRK], z[kRK], w[kRK];
+        const bool full = i0 + kRK <= end;
+        if (full) {
+            load_k<VEC>(P.p[0], P.stride[0], i0, x);
+            if (ND >= 2) load_k<VEC>(P.p[1], P.stride[1], i0, y);
+            if (ND >= 3) load_k<VEC>(P.p[2], P.stride[2], i0, z);
+            if (W) load_k<VEC>(P.p[3], P.stride[3], i0, w);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kRK; ++j) {
+                const bool in = i0 + j < end;
+                x[j] = in ? P.p[0][(i0 + j) * P.stride[0]] : 0.0;
+                if (ND >= 2) y[j] = in ? P.p[1][(i0 + j) * P.stride[1]] : 0.0;
+                if (ND >= 3) z[j] = in ? P.p[2][(i0 + j) * P.stride[2]] : 0.0;
+                if (W) w[j] = in ? P.p[3][(i0 + j) * P.stride[3]] : 0.0;
+            }
+        }
+        int cur = -1;                 // base cell of the open run, -1 = none
+        double acc[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+#pragma unroll
+        for (int j = 0; j < kRK; ++j) {
+            int b[3] = {0, 0, 0};
+            double wx[NW], wy[NW], wz[NW];
+            bool ok = i0 + j < end;
+            if constexpr (S == 0) {
+                ok = ngp_axis(x[j], P.lo[0], P.inv[0], P.fbins[0], b[0]) && ok;
+                if (ND >= 2) ok = ngp_axis(y[j], P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
+                if (ND >= 3) ok = ngp_axis(z[j], P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
+                wx[0] = wy[0] = wz[0] = 1.0;
+            } else {
+                double (&rx)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wx);
+                double (&ry)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wy);
+                double (&rz)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wz);
+                ok = shape_axis<SS, false>(x[j], P.lo[0], P.inv[0], P.fbins_p1[0], b[0], rx) && ok;
+                if (ND >= 2) ok = shape_axis<SS, true>(y[j], P.lo[1], P.inv[1], P.fbins_p1[1], b[1], ry) && ok;
+                if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z[j], P.lo[2], P.inv[2], P.fbins_p1[2], b[2], rz) && ok;
+            }
+            if (!ok) continue;
+            const int key = (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2];      // dims beyond ndim are 1
+            const bool same = key == cur;
+            if (!same && cur >= 0) commit(cur, acc);
+            cur = key;
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int d = 0; d < NDD; ++d) {
+                        double v;
+                        if (S == 0) v = W ? w[j] : 1.0;
+                        else if (ND == 1) v = W ? __dmul_rn(wx[a], w[j]) : wx[a];
+                        else {
+                            v = __dmul_rn(wx[a], wy[c]);
+                            if (ND == 3) v = __dmul_rn(v, wz[d]);
+                            if (W) v = __dmul_rn(v, w[j]);
+                        }
+                        const int k = (a * NC + c) * NDD + d;
+                        acc[k] = same ? __dadd_rn(acc[k], v) : v;
+                    }
+        }
+        // merge the runs still open at the end of each lane's K particles across the warp
+        const int key = cur >= 0 ? cur : -1 - lane;
+        const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = lane == 0 || prev != key;
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        bool mine = cur >= 0;
+        if (__popc(heads) <= 20) {
+            const unsigned above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
+            const int next_head = above ? __ffs(above) - 1 : 32;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const bool take = lane + dd < next_head;
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    const double o = __shfl_down_sync(0xffffffffu, acc[k], dd);
+                    if (take) acc[k] = __dadd_rn(acc[k], o);
+                }
+            }
+            mine = mine && head;
+        }
+        if (mine) commit(cur, acc);
+    }
+}
+
+template <int ND, int S, bool W>
+static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, int sm_count, cudaStream_t st) {
+    if (P.n <= 0) return cudaSuccess;
+    bool vec = true;
+    const int nd_arrays = ND + (W ? 1 : 0);
+    for (int k = 0; k < 4; ++k) {
+        const bool used = k < ND || (k == 3 && W);
+        if (!used) continue;
+        if (P.stride[k] != 1 || (reinterpret_cast<uintptr_t>(P.p[k]) & 15u)) vec = false;
+    }
+    (void)nd_arrays;
+    int64_t want = (P.n + (int64_t)kRT * kRK - 1) / ((int64_t)kRT * kRK);
+    int64_t cap = (int64_t)sm_count * 4;
+    int blocks = (int)(want < cap ? want : cap);
+    if (blocks < 1) blocks = 1;
+    if (vec) k_deposit_runs<ND, S, W, true><<<blocks, kRT, 0, st>>>(P, gate);
+    else k_deposit_runs<ND, S, W, false><<<blocks, kRT, 0, st>>>(P, gate);
+    return cudaGetLastError();
+}
+
+template <int ND, int S>
+static cudaError_t runs_w(const DepositParams &P, const TileConfig *gate, int sm, cudaStream_t st) {
+    return P.p[3] ? launch_runs<ND, S, true>(P, gate, sm, st) : launch_runs<ND, S, false>(P, gate, sm, st);
+}
+
+template <int ND>
+static cudaError_t runs_s(int shape, const DepositParams &P, const TileConfig *gate, int sm, cudaStream_t st) {
+    switch (shape) {
+        case 0: return runs_w<ND, 0>(P, gate, sm, st);
+        case 1: return runs_w<ND, 1>(P, gate, sm, st);
+        case 2: return runs_w<ND, 2>(P, gate, sm, st);
+        default: return runs_w<ND, 3>(P, gate, sm, st);
+    }
+}
+
+cudaError_t deposit_runs(int ndim, int shape, const DepositParams &P, const TileConfig *gate, int sm_count,
+                         cudaStream_t st) {
+    switch (ndim) {
+        case 1: return runs_s<1>(shape, P, gate, sm_count, st);
+        case 2: return runs_s<2>(shape, P, gate, sm_count, st);
+        default: return runs_s<3>(shape, P, gate, sm_count, st);
+    }
+}
+
+}  // namespace ptg

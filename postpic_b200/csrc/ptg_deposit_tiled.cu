@@ -23,7 +23,10 @@
 
 namespace ptg {
 
-constexpr int kTT = 512;                  // threads per CTA, one CTA per SM (<= 128 registers each)
+constexpr int kTT = 512;                  // probe CTA width
+// CTA width of the tiled kernel by stencil size: small stencils need few registers, so more warps
+// can keep shared-memory atomics in flight (one CTA per SM owns the whole 200 KB tile)
+template <int NV> struct TileThreads { static constexpr int value = NV <= 4 ? 1024 : NV <= 9 ? 768 : 512; };
 constexpr int kTileCells = 25600;         // 200 KB of doubles
 constexpr int kProbeBlocks = 16;
 constexpr int kEvalEvery = 4;             // sub-chunks between hit-rate evaluations
@@ -76,6 +79,7 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
     constexpr int NW = StencilWidth<S>::value;
     double mad_sum[3] = {0, 0, 0};
     int blocks_used = 0;
+    long long eq_pairs = 0, all_pairs = 0;
     if (P.n >= 2 * kTT) {
         for (int blk = 0; blk < kProbeBlocks; ++blk) {
             const int64_t start = (P.n - kTT) / (kProbeBlocks - 1) * blk;
@@ -88,6 +92,13 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
             const long long cnt = block_sum(ok ? 1 : 0, scratch);
             if (cnt < 32) continue;
             ++blocks_used;
+            {   // consecutive particles with the same base cell (pairs inside a warp only)
+                const int key = ok ? (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2] : -1;
+                const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+                const bool pair = (threadIdx.x & 31) != 0 && key >= 0 && prev >= 0;
+                eq_pairs += block_sum(pair && key == prev ? 1 : 0, scratch);
+                all_pairs += block_sum(pair ? 1 : 0, scratch);
+            }
             for (int a = 0; a < ND; ++a) {
                 const long long sum = block_sum(ok ? b[a] : 0, scratch);
                 const long long mean = sum / cnt;
@@ -98,8 +109,10 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
     }
     if (threadIdx.x != 0) return;
     TileConfig c;
-    c.useful = 0;
+    c.mode = kModeRows;
     c.est_hit = 0.f;
+    c.run_frac = all_pairs > 0 ? (float)((double)eq_pairs / (double)all_pairs) : 0.f;
+    c.pad[0] = c.pad[1] = 0;
     c.ext[0] = c.ext[1] = c.ext[2] = 1;
     if (blocks_used > 0 || force) {
         double need[3] = {1, 1, 1}, prod = 1;
@@ -134,8 +147,11 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
         double hit = 1;
         for (int a = 0; a < ND; ++a) hit *= fmin(1.0, (double)c.ext[a] / need[a]);
         c.est_hit = (float)hit;
-        c.useful = (hit >= 0.45 || force) ? 1 : 0;
+        if (hit >= 0.45 || force) c.mode = kModeTiled;
     }
+    // long runs of equal base cells: register run-length accumulation beats the tile
+    // (break-even is an average run of ~2.5 particles)
+    if (!force && c.run_frac >= 0.6f) c.mode = kModeRuns;
     *cfg = c;
 }
 
@@ -147,11 +163,14 @@ struct Window {
     int e[3];      // extent
 };
 
-template <int ND>
-__device__ __forceinline__ void flush_tile(double *tile, const Window &wd, const DepositParams &P, int cells) {
-    // merge the tile into the global grid (coalesced along the last axis) and clear it
-    for (int c = threadIdx.x; c < cells; c += kTT) {
-        const double v = tile[c];
+template <int ND, int TT>
+__device__ __forceinline__ void flush_tile(double *tile, const Window &wd, const DepositParams &P, int cells,
+                                           int replicas) {
+    // merge the tile (all its replicas) into the global grid, coalesced along the last axis, and clear it
+    for (int c = threadIdx.x; c < cells; c += TT) {
+        double v = tile[c];
+        tile[c] = 0.0;
+        for (int r = 1; r < replicas; ++r) { v = __dadd_rn(v, tile[r * cells + c]); tile[r * cells + c] = 0.0; }
         if (v != 0.0) {
             int64_t lin;
             if (ND == 1) lin = wd.o[0] + c;
@@ -165,13 +184,12 @@ __device__ __forceinline__ void flush_tile(double *tile, const Window &wd, const
                 lin = ((int64_t)(wd.o[0] + ix) * P.dims[1] + wd.o[1] + iy) * P.dims[2] + wd.o[2] + iz;
             }
             red_add(P.grid + lin, v);
-            tile[c] = 0.0;
         }
     }
 }
 
-template <int ND, int S, bool W>
-__global__ void __launch_bounds__(kTT, 1) k_deposit_tiled(const DepositParams P, const TileConfig *cfgp) {
+template <int ND, int S, bool W, int TT>
+__global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, const TileConfig *cfgp) {
     extern __shared__ double tile[];
     __shared__ long long scratch[34];
     __shared__ Window s_win;
@@ -180,11 +198,18 @@ __global__ void __launch_bounds__(kTT, 1) k_deposit_tiled(const DepositParams P,
     constexpr int SS = S == 0 ? 1 : S;
 
     const TileConfig cfg = *cfgp;
-    if (!cfg.useful) return;
+    if (cfg.mode != kModeTiled) return;
     int cells = 1;
-    for (int a = 0; a < ND; ++a) cells *= cfg.ext[a];
+    bool whole = true;                       // the window holds the whole grid (small 1-D / 2-D histograms)
+    for (int a = 0; a < ND; ++a) { cells *= cfg.ext[a]; whole = whole && cfg.ext[a] >= P.dims[a]; }
+    // a grid that fits several times is replicated: warp w accumulates into replica w % R, which
+    // divides the same-address contention of the shared-memory atomics by R
+    int replicas = whole ? kTileCells / cells : 1;
+    if (replicas > TT / 32) replicas = TT / 32;
+    if (replicas < 1) replicas = 1;
+    double *mytile = tile + ((threadIdx.x >> 5) % replicas) * cells;
 
-    for (int c = threadIdx.x; c < cells; c += kTT) tile[c] = 0.0;
+    for (int c = threadIdx.x; c < cells * replicas; c += TT) tile[c] = 0.0;
     if (threadIdx.x == 0) {
         for (int a = 0; a < 3; ++a) { s_win.e[a] = a < ND ? cfg.ext[a] : 1; s_win.o[a] = 0; }
         // a window that covers the whole axis never needs to move; the others start "nowhere"
@@ -196,7 +221,7 @@ __global__ void __launch_bounds__(kTT, 1) k_deposit_tiled(const DepositParams P,
 
     // contiguous span of this CTA, a multiple of the CTA width
     int64_t per = (P.n + gridDim.x - 1) / gridDim.x;
-    per = (per + kTT - 1) / kTT * kTT;
+    per = (per + TT - 1) / TT * TT;
     const int64_t begin = (int64_t)blockIdx.x * per;
     const int64_t end = begin + per < P.n ? begin + per : P.n;
     const int lane = threadIdx.x & 31;
@@ -216,11 +241,11 @@ __global__ void __launch_bounds__(kTT, 1) k_deposit_tiled(const DepositParams P,
     }
     int since_eval = kEvalEvery - 1;       // first evaluation right after the first sub-chunk
     unsigned acc_w = 0, miss_w = 0;        // per-warp counters (lane 0), published at evaluation time
-    for (int64_t i0 = begin; i0 < end; i0 += kTT) {
+    for (int64_t i0 = begin; i0 < end; i0 += TT) {
         const int64_t i = i0 + threadIdx.x;
         const double x = nx, y = ny, z = nz, w = nwt;
         {
-            const int64_t j = i + kTT;
+            const int64_t j = i + TT;
             if (j < end) {
                 nx = ld_stream(px + j * sx);
                 if (ND >= 2) ny = ld_stream(py + j * sy);
@@ -301,7 +326,7 @@ __global__ void __launch_bounds__(kTT, 1) k_deposit_tiled(const DepositParams P,
         for (int a = 0; a < ND; ++a) hit = hit && b[a] >= wd.o[a] && b[a] + NW <= wd.o[a] + wd.e[a];
         if (hit) {
             const int p1 = ND >= 2 ? wd.e[1] : 1, p2 = ND >= 3 ? wd.e[2] : 1;
-            double *t = tile + ((b[0] - wd.o[0]) * p1 + (ND >= 2 ? b[1] - wd.o[1] : 0)) * p2 + (ND >= 3 ? b[2] - wd.o[2] : 0);
+            double *t = mytile + ((b[0] - wd.o[0]) * p1 + (ND >= 2 ? b[1] - wd.o[1] : 0)) * p2 + (ND >= 3 ? b[2] - wd.o[2] : 0);
 #pragma unroll
             for (int a = 0; a < NA; ++a)
 #pragma unroll
@@ -326,7 +351,7 @@ __global__ void __launch_bounds__(kTT, 1) k_deposit_tiled(const DepositParams P,
         const unsigned m_in = __ballot_sync(0xffffffffu, inside);
         acc_w += __popc(m_ok);
         miss_w += __popc(m_ok & ~m_in);
-        if (++since_eval == kEvalEvery && i0 + kTT < end) {
+        if (++since_eval == kEvalEvery && i0 + TT < end) {
             since_eval = 0;
             if (threadIdx.x == 0) { s_acc = 0; s_miss = 0; }
             __syncthreads();
@@ -337,7 +362,7 @@ __global__ void __launch_bounds__(kTT, 1) k_deposit_tiled(const DepositParams P,
             const bool move = acc >= 64 && miss * 2 > acc;
             __syncthreads();
             if (move) {
-                flush_tile<ND>(tile, wd, P, cells);
+                flush_tile<ND, TT>(tile, wd, P, cells, replicas);
                 // new centre: mean base cell of the sub-chunk in registers
                 const long long cnt = block_sum(ok ? 1 : 0, scratch);
                 long long mean[3] = {0, 0, 0};
@@ -358,7 +383,7 @@ __global__ void __launch_bounds__(kTT, 1) k_deposit_tiled(const DepositParams P,
         }
     }
     __syncthreads();
-    flush_tile<ND>(tile, wd, P, cells);
+    flush_tile<ND, TT>(tile, wd, P, cells, replicas);
 }
 
 // ---------------------------------------------------------------------------------
@@ -366,13 +391,15 @@ __global__ void __launch_bounds__(kTT, 1) k_deposit_tiled(const DepositParams P,
 // ---------------------------------------------------------------------------------
 template <int ND, int S, bool W>
 static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int force, int sm_count, cudaStream_t st) {
-    auto kern = k_deposit_tiled<ND, S, W>;
+    constexpr int NW = StencilWidth<S>::value;
+    constexpr int TT = TileThreads<(ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW)>::value;
+    auto kern = k_deposit_tiled<ND, S, W, TT>;
     const size_t smem = (size_t)kTileCells * sizeof(double);
     // per-device attribute, cheap to set: done on every launch so that any device works
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_probe<ND, S><<<1, kTT, 0, st>>>(P, cfg, force);
-    kern<<<sm_count, kTT, smem, st>>>(P, cfg);
+    kern<<<sm_count, TT, smem, st>>>(P, cfg);
     return cudaGetLastError();
 }
 

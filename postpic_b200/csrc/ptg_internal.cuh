@@ -9,21 +9,28 @@ namespace ptg {
 
 // Decision record of the probe kernel (device memory): whether a shared-memory tile pays off
 // for this launch and the window extents it chose.
+enum : int { kModeRows = 0, kModeTiled = 1, kModeRuns = 2 };
+
 struct TileConfig {
-    int useful;
-    int ext[3];
-    float est_hit;
-    int pad[3];
+    int mode;          // which of the kernels launched for an AUTO call does the work
+    int ext[3];        // tile window extents chosen for kModeTiled
+    float est_hit;     // estimated fraction of particles that fall into such a window
+    float run_frac;    // fraction of consecutive particle pairs with equal stencil base cell
+    int pad[2];
 };
 
-// ptg_deposit_global.cu -- `gate` (nullable): the kernels return at once when gate->useful != 0,
-// i.e. when the tiled kernel launched next to them is doing the work.
+// ptg_deposit_global.cu -- `gate` (nullable): the kernels return at once unless gate->mode is
+// kModeRows, i.e. when one of the kernels launched next to them is doing the work.
 cudaError_t deposit_global(int ndim, int shape, const DepositParams &P, bool rows, const TileConfig *gate,
                            int sm_count, cudaStream_t st);
 
 // ptg_deposit_tiled.cu -- probe + tiled kernel; `force` ignores the probe's verdict
 cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, int sm_count,
                           cudaStream_t st);
+
+// ptg_deposit_runs.cu -- run-length accumulation in registers for cell-ordered input
+cudaError_t deposit_runs(int ndim, int shape, const DepositParams &P, const TileConfig *gate, int sm_count,
+                         cudaStream_t st);
 
 // ptg_deposit_sorted.cu -- deterministic sort-by-cell + segmented reduce; needs a workspace of
 // sorted_workspace_bytes(n, cells) bytes

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "ptg_golden.npz"))
 ALL = [(nd, s, w) for nd in (1, 2, 3) for s in (0, 1, 2, 3) for w in (False, True)]
-METHODS = [None, 'global', 'rows', 'tiled', 'sorted']
+METHODS = [None, 'global', 'rows', 'tiled', 'sorted', 'runs']
 
 
 @pytest.fixture(scope="module")
@@ -316,7 +316,7 @@ def test_large_properties_on_device(shape):
     # methods agree
     if shape:
         ga, _ = device.deposit([x, y], w, method='global', **kw)
-        for m in ('rows', 'tiled', 'sorted'):
+        for m in ('rows', 'tiled', 'sorted', 'runs'):
             gb, _ = device.deposit([x, y], w, method=m, **kw)
             assert float((ga - gb).abs().max()) <= 1e-12 * float(grid.abs().max())
         # x-sorted and cell-sorted orders exercise the tile window moves and the warp aggregation
@@ -327,8 +327,13 @@ def test_large_properties_on_device(shape):
         order = torch.argsort(cell)
         gc, _ = device.deposit([x[order], y[order]], w[order], method='tiled', **kw)
         assert float((gc - grid).abs().max()) <= 1e-12 * float(grid.abs().max())
-        gc, _ = device.deposit([x[order], y[order]], w[order], method=None, **kw)
-        assert float((gc - grid).abs().max()) <= 1e-12 * float(grid.abs().max())
+        for m in (None, 'runs'):
+            gc, _ = device.deposit([x[order], y[order]], w[order], method=m, **kw)
+            assert float((gc - grid).abs().max()) <= 1e-12 * float(grid.abs().max())
+        # unaligned / strided views take the scalar-load variant of the runs kernel
+        gc, _ = device.deposit([x[order][1:], y[order][1:]], w[order][1:], method='runs', **kw)
+        g1, _ = device.deposit([x[order][1:], y[order][1:]], w[order][1:], method='global', **kw)
+        assert float((gc - g1).abs().max()) <= 1e-12 * float(grid.abs().max())
 
 
 @pytest.mark.parametrize("nd,shape", [(1, 1), (2, 0), (2, 2), (2, 3), (3, 1), (3, 3)])
