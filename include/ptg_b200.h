@@ -101,8 +101,8 @@ size_t ptg_workspace_bytes(int ndim, int shape, int64_t n, const int *bins, unsi
 int64_t ptg_padded_cells(int ndim, int shape, const int *bins);
 
 /* ---- helpers on device buffers ------------------------------------------------------ */
-/* out2[0] = min, out2[1] = max over x[0..n) (device pointer out2; NaNs are ignored like
- * they are not by np.min -- see INTEGRATION.md); replaces _routines.py:117-126.        */
+/* out2[0] = min, out2[1] = max over x[0..n) (out2: device pointer to 2 doubles).  A NaN
+ * anywhere yields NaN for both, like np.min/np.max; replaces _routines.py:117-126.     */
 int ptg_minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, void *stream);
 /* grid[i] *= factor for i in [0,count): the h /= dV of particles.py:1101-1102 with
  * factor = 1/dV computed by the caller.                                               */

@@ -122,6 +122,8 @@ void fill_params(ptg::DepositParams &P, int ndim, int shape, int64_t n, const do
         P.dims[a] = on ? bins[a] + 2 * shape : 1;
     }
     P.grid = grid;
+    P.slab_lo = -(1 << 30);
+    P.slab_hi = 1 << 30;
 }
 
 constexpr unsigned kCfgRing = 256;
@@ -134,6 +136,7 @@ int next_tile_config(DeviceState *d, ptg::TileConfig **out) {
         if (!d->cfg_ring) {
             ptg::TileConfig *ring = nullptr;
             PTG_CUDA(cudaMalloc(&ring, kCfgRing * sizeof(ptg::TileConfig)));
+            PTG_CUDA(cudaMemset(ring, 0, kCfgRing * sizeof(ptg::TileConfig)));   // tickets start at 0
             d->cfg_ring = ring;
         }
     }

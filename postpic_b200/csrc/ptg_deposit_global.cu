@@ -13,6 +13,8 @@
 //                   lanes of one RED instruction cover whole stencil rows: S+1 adjacent
 //                   lanes hit S+1 adjacent doubles (one or two sectors) and the LSU
 //                   coalesces them into one L2 request per sector.
+#include <cstdlib>
+
 #include "ptg_internal.cuh"
 
 namespace ptg {
@@ -31,7 +33,7 @@ __device__ __forceinline__ void deposit_particle_global(const DepositParams &P, 
         bool ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], cx);
         if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], cy) && ok;
         if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], cz) && ok;
-        if (!ok) return;
+        if (!ok || cx < P.slab_lo || cx >= P.slab_hi) return;
         int64_t lin = cx;
         if (ND >= 2) lin = lin * P.dims[1] + cy;
         if (ND >= 3) lin = lin * P.dims[2] + cz;
@@ -45,7 +47,7 @@ __device__ __forceinline__ void deposit_particle_global(const DepositParams &P, 
     bool ok = shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], bx, wx);
     if (ND >= 2) ok = shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], by, wy) && ok;
     if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], bz, wz) && ok;
-    if (!ok) return;
+    if (!ok || bx < P.slab_lo || bx >= P.slab_hi) return;
     if (ND == 1) {
         double *g = P.grid + bx;
 #pragma unroll
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
             ok = shape_axis<S, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], bx, wx);
             if (ND >= 2) ok = shape_axis<S, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], by, wy) && ok;
             if (ND >= 3) ok = shape_axis<S, (S == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], bz, wz) && ok;
+            ok = ok && bx >= P.slab_lo && bx < P.slab_hi;
         }
         int lin0 = -1;                                    // padded linear index of the first cell
         if (ok) lin0 = ND == 1 ? bx : ND == 2 ? bx * P.dims[1] + by : (bx * P.dims[1] + by) * P.dims[2] + bz;
@@ -253,13 +256,53 @@ static cudaError_t dispatch_s(int shape, const DepositParams &P, bool rows, cons
     }
 }
 
-cudaError_t deposit_global(int ndim, int shape, const DepositParams &P, bool rows, const TileConfig *gate,
-                           int sm_count, cudaStream_t st) {
+static cudaError_t deposit_global_pass(int ndim, int shape, const DepositParams &P, bool rows, const TileConfig *gate,
+                                       int sm_count, cudaStream_t st) {
     switch (ndim) {
         case 1: return dispatch_s<1>(shape, P, rows, gate, sm_count, st);
         case 2: return dispatch_s<2>(shape, P, rows, gate, sm_count, st);
         default: return dispatch_s<3>(shape, P, rows, gate, sm_count, st);
     }
+}
+
+// Grids that do not fit in L2 (e.g. 258^3 doubles = 137 MB vs 126 MB) make most reductions miss:
+// measured 58 G sector-REDs/s against 190 G/s on an L2-resident grid.  Such grids are deposited
+// in slab passes: every pass streams all particles again but only deposits those whose base
+// cell on axis 0 falls in the pass's slab, so the reductions of a pass hit an L2-resident
+// slice of <= 72 MiB (sweep in profiles/README.md: 24/36/48/72/100/200 MiB -> 9.7/14.4/18.9/21.8/
+// 21.8/11.1 Gp/s for 3-D CIC on 258^3).  Re-reading 32 B/particle per pass is cheaper than the misses.
+static int64_t slab_bytes() {
+    static int64_t v = 0;
+    if (v == 0) {
+        const char *e = getenv("PTG_SLAB_MB");            // tuning knob; default 72 MiB (measured best for 258^3)
+        int64_t mb = e ? atoll(e) : 72;
+        if (mb < 1) mb = 1;
+        v = mb << 20;
+    }
+    return v;
+}
+
+cudaError_t deposit_global(int ndim, int shape, const DepositParams &P0, bool rows, const TileConfig *gate,
+                           int sm_count, cudaStream_t st) {
+    DepositParams P = P0;
+    const int64_t row_bytes = (int64_t)P.dims[1] * P.dims[2] * 8;          // one axis-0 slice
+    const int64_t grid_bytes = row_bytes * P.dims[0];
+    int passes = 1;
+    const int64_t kSlabBytes = slab_bytes();
+    if (grid_bytes > 96 * (int64_t(1) << 20) && P.n >= (int64_t(1) << 22)) passes = (int)((grid_bytes + kSlabBytes - 1) / kSlabBytes);
+    if (passes > P.dims[0]) passes = P.dims[0];
+    if (passes <= 1) {
+        P.slab_lo = -(1 << 30);
+        P.slab_hi = 1 << 30;
+        return deposit_global_pass(ndim, shape, P, rows, gate, sm_count, st);
+    }
+    for (int s = 0; s < passes; ++s) {
+        P.slab_lo = s == 0 ? -(1 << 30) : (int)((int64_t)P.dims[0] * s / passes);
+        P.slab_hi = s == passes - 1 ? (1 << 30) : (int)((int64_t)P.dims[0] * (s + 1) / passes);
+        cudaError_t e = deposit_global_pass(ndim, shape, P, rows, gate, sm_count, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 }  // namespace ptg

@@ -26,7 +26,10 @@ constexpr int kRT = 256;      // threads per CTA
 constexpr int kRK = 4;        // consecutive particles per thread
 
 __device__ __forceinline__ void ld_stream_v2(const double *p, double &a, double &b) {
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(a), "=d"(b) : "l"(p), "l"(pol));
 }
 
 // K consecutive values starting at element i (all K valid)

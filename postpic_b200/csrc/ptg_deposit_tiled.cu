@@ -28,7 +28,6 @@ constexpr int kTT = 512;                  // probe CTA width
 // can keep shared-memory atomics in flight (one CTA per SM owns the whole 200 KB tile)
 template <int NV> struct TileThreads { static constexpr int value = NV <= 4 ? 1024 : NV <= 9 ? 768 : 512; };
 constexpr int kTileCells = 25600;         // 200 KB of doubles
-constexpr int kProbeBlocks = 16;
 constexpr int kEvalEvery = 4;             // sub-chunks between hit-rate evaluations
 
 // ---------------------------------------------------------------------------------
@@ -76,13 +75,16 @@ __device__ __forceinline__ bool base_cells(const DepositParams &P, double x, dou
 template <int ND, int S>
 __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig *cfg, int force) {
     __shared__ long long scratch[34];
+    __shared__ bool s_last;
     constexpr int NW = StencilWidth<S>::value;
-    double mad_sum[3] = {0, 0, 0};
-    int blocks_used = 0;
-    long long eq_pairs = 0, all_pairs = 0;
-    if (P.n >= 2 * kTT) {
-        for (int blk = 0; blk < kProbeBlocks; ++blk) {
-            const int64_t start = (P.n - kTT) / (kProbeBlocks - 1) * blk;
+    // one probe CTA per block of kTT consecutive particles; the last CTA to finish decides
+    {
+        TileConfig::Part part;
+        part.mad[0] = part.mad[1] = part.mad[2] = 0.f;
+        part.cnt = part.eq_pairs = part.all_pairs = 0;
+        part.pad[0] = part.pad[1] = 0;
+        if (P.n >= 2 * kTT) {
+            const int64_t start = (P.n - kTT) / (kProbeBlocks - 1) * blockIdx.x;
             const int64_t i = start + threadIdx.x;
             const double x = ld_stream(P.p[0] + i * P.stride[0]);
             const double y = ND >= 2 ? ld_stream(P.p[1] + i * P.stride[1]) : 0.0;
@@ -90,29 +92,48 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
             int b[3];
             const bool ok = base_cells<ND, S>(P, x, y, z, b);
             const long long cnt = block_sum(ok ? 1 : 0, scratch);
-            if (cnt < 32) continue;
-            ++blocks_used;
-            {   // consecutive particles with the same base cell (pairs inside a warp only)
+            if (cnt >= 32) {
+                part.cnt = (int)cnt;
+                // consecutive particles with the same base cell (pairs inside a warp only)
                 const int key = ok ? (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2] : -1;
                 const int prev = __shfl_up_sync(0xffffffffu, key, 1);
                 const bool pair = (threadIdx.x & 31) != 0 && key >= 0 && prev >= 0;
-                eq_pairs += block_sum(pair && key == prev ? 1 : 0, scratch);
-                all_pairs += block_sum(pair ? 1 : 0, scratch);
-            }
-            for (int a = 0; a < ND; ++a) {
-                const long long sum = block_sum(ok ? b[a] : 0, scratch);
-                const long long mean = sum / cnt;
-                const long long dev = block_sum(ok ? llabs((long long)b[a] - mean) : 0, scratch);
-                mad_sum[a] += (double)dev / (double)cnt;
+                part.eq_pairs = (int)block_sum(pair && key == prev ? 1 : 0, scratch);
+                part.all_pairs = (int)block_sum(pair ? 1 : 0, scratch);
+                for (int a = 0; a < ND; ++a) {
+                    const long long sum = block_sum(ok ? b[a] : 0, scratch);
+                    const long long mean = sum / cnt;
+                    const long long dev = block_sum(ok ? llabs((long long)b[a] - mean) : 0, scratch);
+                    part.mad[a] = (float)((double)dev / (double)cnt);
+                }
             }
         }
+        if (threadIdx.x == 0) {
+            cfg->part[blockIdx.x] = part;
+            __threadfence();
+            const unsigned t = atomicAdd(&cfg->ticket, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+    }
+    double mad_sum[3] = {0, 0, 0};
+    int blocks_used = 0;
+    long long eq_pairs = 0, all_pairs = 0;
+    for (int blk = 0; blk < (int)gridDim.x; ++blk) {
+        const volatile TileConfig::Part *q = &cfg->part[blk];
+        if (q->cnt < 32) continue;
+        ++blocks_used;
+        for (int a = 0; a < ND; ++a) mad_sum[a] += q->mad[a];
+        eq_pairs += q->eq_pairs;
+        all_pairs += q->all_pairs;
     }
     if (threadIdx.x != 0) return;
-    TileConfig c;
+    struct { int mode; int ext[3]; float est_hit; float run_frac; } c;
     c.mode = kModeRows;
     c.est_hit = 0.f;
     c.run_frac = all_pairs > 0 ? (float)((double)eq_pairs / (double)all_pairs) : 0.f;
-    c.pad[0] = c.pad[1] = 0;
     c.ext[0] = c.ext[1] = c.ext[2] = 1;
     if (blocks_used > 0 || force) {
         double need[3] = {1, 1, 1}, prod = 1;
@@ -147,12 +168,23 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
         double hit = 1;
         for (int a = 0; a < ND; ++a) hit *= fmin(1.0, (double)c.ext[a] / need[a]);
         c.est_hit = (float)hit;
-        if (hit >= 0.45 || force) c.mode = kModeTiled;
+        // A band of whole rows (x-ordered input, uniform along the last axis) is no win: its
+        // shared-memory CAS atomics run at about the rate of the L2 reductions of method ROWS
+        // (measured 36 vs 38 Gp/s, 2-D TSC).  The tile pays off when it is a true window on the
+        // last axis (bunches), or when the whole grid fits (1-D and small histograms).
+        bool whole = true;
+        for (int a = 0; a < ND; ++a) whole = whole && c.ext[a] >= P.dims[a];
+        const bool windowed_last = c.ext[ND - 1] < P.dims[ND - 1];
+        if (force || (hit >= 0.45 && (whole || windowed_last || ND == 1))) c.mode = kModeTiled;
     }
     // long runs of equal base cells: register run-length accumulation beats the tile
     // (break-even is an average run of ~2.5 particles)
     if (!force && c.run_frac >= 0.6f) c.mode = kModeRuns;
-    *cfg = c;
+    cfg->mode = c.mode;
+    for (int a = 0; a < 3; ++a) cfg->ext[a] = c.ext[a];
+    cfg->est_hit = c.est_hit;
+    cfg->run_frac = c.run_frac;
+    cfg->ticket = 0;                      // ready for the next call that gets this ring entry
 }
 
 // ---------------------------------------------------------------------------------
@@ -398,7 +430,7 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
     // per-device attribute, cheap to set: done on every launch so that any device works
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_probe<ND, S><<<1, kTT, 0, st>>>(P, cfg, force);
+    k_probe<ND, S><<<kProbeBlocks, kTT, 0, st>>>(P, cfg, force);
     kern<<<sm_count, TT, smem, st>>>(P, cfg);
     return cudaGetLastError();
 }

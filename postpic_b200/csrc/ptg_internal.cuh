@@ -11,12 +11,17 @@ namespace ptg {
 // for this launch and the window extents it chose.
 enum : int { kModeRows = 0, kModeTiled = 1, kModeRuns = 2 };
 
+constexpr int kProbeBlocks = 16;
+
 struct TileConfig {
     int mode;          // which of the kernels launched for an AUTO call does the work
     int ext[3];        // tile window extents chosen for kModeTiled
     float est_hit;     // estimated fraction of particles that fall into such a window
     float run_frac;    // fraction of consecutive particle pairs with equal stencil base cell
-    int pad[2];
+    unsigned ticket;   // probe CTAs that have finished (reset to 0 by the last one)
+    int pad;
+    // per-probe-CTA partial statistics
+    struct Part { float mad[3]; int cnt; int eq_pairs; int all_pairs; int pad[2]; } part[kProbeBlocks];
 };
 
 // ptg_deposit_global.cu -- `gate` (nullable): the kernels return at once unless gate->mode is

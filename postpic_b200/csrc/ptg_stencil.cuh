@@ -106,13 +106,19 @@ struct DepositParams {
     int bins[3];
     int dims[3];            // padded dims = bins + 2*shape
     double *grid;
+    // slab pass (methods GLOBAL / ROWS on grids larger than L2): only particles whose stencil base
+    // cell on axis 0 lies in [slab_lo, slab_hi) are deposited by this launch
+    int slab_lo, slab_hi;
 };
 
-// Streaming 8-byte load: read-only path, do not allocate in L1 (each particle is
-// touched exactly once).
+// Streaming 8-byte load: read-only path, do not allocate in L1 and mark the line evict-first
+// in L2 (each particle is touched exactly once; the L2 belongs to the grid the reductions
+// hit).  ptxas folds the policy into the load's descriptor, it costs no instruction.
 __device__ __forceinline__ double ld_stream(const double *p) {
     double v;
-    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
 }
 

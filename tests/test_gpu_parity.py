@@ -358,3 +358,20 @@ def test_sorted_method_is_bit_reproducible(nd, shape):
     assert torch.equal(g1, g2) and torch.equal(g1, g3)
     ga, _ = device.deposit(coords, w, method='global', **kw)
     assert float((g1 - ga).abs().max()) <= 1e-12 * float(ga.abs().max())
+
+
+def test_slab_passes_on_a_grid_larger_than_l2():
+    """3-D grid of 242^3 doubles = 113 MB: methods rows / global deposit it in slab passes over
+    axis 0; the un-slabbed runs kernel is the cross-check."""
+    import torch
+    from postpic_b200 import device
+    n = 6_000_000
+    g = torch.Generator(device='cuda').manual_seed(77)
+    c = [torch.rand(n, dtype=torch.float64, device='cuda', generator=g) * 1.02 - 0.01 for _ in range(3)]
+    w = torch.rand(n, dtype=torch.float64, device='cuda', generator=g)
+    kw = dict(range=[(0, 1)] * 3, bins=(240, 240, 240), shape=1)
+    ref, plan = device.deposit(c, w, method='runs', **kw)
+    for m in ('rows', 'global', None):
+        got, _ = device.deposit(c, w, method=m, **kw)
+        assert float((got - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+        assert abs(float(got.sum()) - float(ref.sum())) <= 1e-12 * float(w.sum())
