@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--n", type=float, default=None, help="particles per GPU (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--cpu-sample", type=float, default=2e7)
     ap.add_argument("--e2e-steps", type=int, default=None)
     return ap.parse_args()
@@ -408,6 +409,31 @@ def run_b200_arm(args):
                "api": "postpic_b200.histogramdd(numpy views of pinned host memory)" if world == 1 else
                       "pinned host -> device copy + postpic_b200.parallel.deposit_sharded + grid D2H"}
 
+    # the same workload in the two particle orders PIC dumps come in:
+    # device-timed like `value`; reported next to the headline, never instead of it
+    variants = None
+    if world == 1 and not args.no_variants and args.order == "random":
+        variants = {}
+        del coords, w
+        torch.cuda.empty_cache()
+        for order in ("sorted", "cellsorted"):
+            vc, vw = make_cloud_device(name, n, 2 + rank, order, dev)
+            for _ in range(3):
+                ptgdev.deposit_into(grid, plan, vc, vw, method=method, zero=True)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(args.steps):
+                ptgdev.deposit_into(grid, plan, vc, vw, method=method, zero=True)
+            b.record()
+            b.synchronize()
+            ms = a.elapsed_time(b) / args.steps
+            variants["x_sorted" if order == "sorted" else "cell_sorted"] = {
+                "value": n / (ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": ms,
+                "roofline_frac": n * bpp / (ms * 1e-3) * 1e-9 / peak}
+            del vc, vw
+            torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = time_cpu(name, int(min(args.cpu_sample, n)))
@@ -422,7 +448,7 @@ def run_b200_arm(args):
                        "l2": "inputs (%.1f GB per GPU) larger than L2, no flush needed" % (n * bpp * 1e-9),
                        "parallelism": "particles sharded over %d GPU(s), private grids, NCCL all-reduce" % world
                        if world > 1 else "1 GPU", "device": info["name"], "sm_count": info["sm_count"]},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "variants": variants,
             "gpu_launches": args.steps * world * {"auto": 4, "tiled": 2}.get(args.method, 1),
             "clocks": clocks.summary(),
             "parity": {"mass_conservation_rel_err": mass_err},

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libptg_b200.so")
+LIB_PATH = os.environ.get("PTG_B200_LIB") or os.path.join(_PKG, "lib", "libptg_b200.so")   # env: A/B builds
 
 PTG_OK = 0
 PTG_EINVAL = -1

@@ -77,6 +77,15 @@ int probe(int device, DeviceState **out) {
             d.cc_major = p.major;
             d.cc_minor = p.minor;
             d.usable = (p.major == 10);           // the library holds sm_100a code only
+            // stream-ordered scratch (staggered staging grid, SORTED workspace) comes from the
+            // device's default memory pool: keep freed blocks cached instead of returning them
+            // to the driver at every synchronisation
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            (void)cudaGetLastError();
             d.probed = true;
         }
     }
@@ -124,6 +133,9 @@ void fill_params(ptg::DepositParams &P, int ndim, int shape, int64_t n, const do
     P.grid = grid;
     P.slab_lo = -(1 << 30);
     P.slab_hi = 1 << 30;
+    P.stag = nullptr;
+    P.stag_pitch = 0;
+    P.stag_copy = 0;
 }
 
 constexpr unsigned kCfgRing = 256;

@@ -130,7 +130,7 @@ template <int ND, int S> struct RowsCfg {
     static constexpr int ITERS = ROWS * G;
 };
 
-template <int ND, int S, bool W>
+template <int ND, int S, bool W, bool STAG>
 __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P, const TileConfig *gate) {
     if (gate != nullptr && gate->mode != kModeRows) return;
     using C = RowsCfg<ND, S>;
@@ -143,8 +143,11 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
     const int64_t nthreads = (int64_t)gridDim.x * kThreads;
     const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
     const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2], sw = P.stride[3];
-    const int row_stride = ND == 1 ? 0 : P.dims[ND - 1];             // between rows of a slab
-    const int slab_stride = ND == 3 ? P.dims[1] * P.dims[2] : 0;
+    // geometry of the array the reductions go to: the padded grid itself, or the staggered staging grid
+    const int pitch = STAG ? P.stag_pitch : P.dims[ND - 1];
+    const int row_stride = ND == 1 ? 0 : pitch;                      // between rows of a slab
+    const int slab_stride = ND == 3 ? P.dims[1] * pitch : 0;
+    double *const target = STAG ? P.stag : P.grid;
 
     // warp-uniform trip count so that the warp-level exchanges stay convergent
     const int64_t first = (int64_t)blockIdx.x * kThreads + warp * 32;
@@ -165,7 +168,16 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
             ok = ok && bx >= P.slab_lo && bx < P.slab_hi;
         }
         int lin0 = -1;                                    // padded linear index of the first cell
-        if (ok) lin0 = ND == 1 ? bx : ND == 2 ? bx * P.dims[1] + by : (bx * P.dims[1] + by) * P.dims[2] + bz;
+        if (ok) {
+            const int col = ND == 1 ? bx : ND == 2 ? by : bz;          // first cell of the rows on the last axis
+            const int rowlin = ND == 1 ? 0 : ND == 2 ? bx : bx * P.dims[1] + by;
+            lin0 = rowlin * pitch + col;
+            if (STAG) {
+                // rows of 3 straddle a sector when col mod 4 is 2 or 3, rows of 2 when it is 3
+                const bool second = NW == 3 ? (col & 2) != 0 : (col & 3) == 3;
+                if (second) lin0 += (int)P.stag_copy + 2;
+            }
+        }
 
 #pragma unroll
         for (int slab = 0; slab < C::SLABS; ++slab) {
@@ -202,11 +214,25 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
                 const int l0 = __shfl_sync(0xffffffffu, lin0, p);
                 if (j < NW && l0 >= 0) {
                     const double v = stage[p * C::PS + row * NW + j];
-                    red_add(P.grid + (int64_t)l0 + (int64_t)slab * slab_stride + row * row_stride + j, v);
+                    red_add(target + (int64_t)l0 + (int64_t)slab * slab_stride + row * row_stride + j, v);
                 }
             }
             __syncwarp();
         }
+    }
+}
+
+// grid[r][j] += stag0[r][j] + stag1[r][j + 2]   (rows = product of all but the last axis)
+__global__ void __launch_bounds__(256) k_merge_staggered(const DepositParams P, int64_t rows, int last,
+                                                          const TileConfig *gate) {
+    if (gate != nullptr && gate->mode != kModeRows) return;
+    const int64_t total = rows * last, step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+        const int64_t r = i / last;
+        const int j = (int)(i - r * last);
+        const double a = P.stag[r * P.stag_pitch + j], b = P.stag[P.stag_copy + r * P.stag_pitch + j + 2];
+        // RED, not a plain store: other streams (the host pipeline's chunks) may be merging into the same grid
+        if (a != 0.0 || b != 0.0) red_add(P.grid + i, __dadd_rn(a, b));
     }
 }
 
@@ -231,7 +257,17 @@ static cudaError_t launch_rows(const DepositParams &P, const TileConfig *gate, i
     int64_t cap = (int64_t)sm_count * 8;
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
-    k_deposit_rows<ND, S, W><<<blocks, kThreads, 0, st>>>(P, gate);
+    if (P.stag != nullptr) {
+        if constexpr (S == 1 || S == 2) {
+            k_deposit_rows<ND, S, W, true><<<blocks, kThreads, 0, st>>>(P, gate);
+            const int last = P.dims[ND - 1];
+            const int64_t rows = (int64_t)P.dims[0] * P.dims[1] * P.dims[2] / last;
+            int64_t mb = (rows * last + 255) / 256;
+            k_merge_staggered<<<(int)(mb < cap ? mb : cap), 256, 0, st>>>(P, rows, last, gate);
+            return cudaGetLastError();
+        }
+    }
+    k_deposit_rows<ND, S, W, false><<<blocks, kThreads, 0, st>>>(P, gate);
     return cudaGetLastError();
 }
 
@@ -294,6 +330,28 @@ cudaError_t deposit_global(int ndim, int shape, const DepositParams &P0, bool ro
     if (passes <= 1) {
         P.slab_lo = -(1 << 30);
         P.slab_hi = 1 << 30;
+        // staggered staging grid: stencil rows of 2 or 3 cells, both copies L2-resident, enough
+        // particles to pay for clearing and merging it
+        static const bool no_stagger = getenv("PTG_NO_STAGGER") != nullptr;
+        const int last = P.dims[ndim - 1];
+        const int pitch = (last + 2 + 3) / 4 * 4;
+        const int64_t nrows = (int64_t)P.dims[0] * P.dims[1] * P.dims[2] / last;
+        const int64_t copy = nrows * pitch + 4;
+        const size_t bytes = (size_t)(2 * copy) * sizeof(double);
+        if (rows && !no_stagger && (shape == 1 || shape == 2) && bytes <= ((size_t)64 << 20) && 2 * copy < (int64_t(1) << 31) &&
+            P.n >= (int64_t(1) << 20)) {
+            void *buf = nullptr;
+            cudaError_t e = cudaMallocAsync(&buf, bytes, st);           // stream-ordered, pooled: no sync
+            if (e != cudaSuccess) return e;
+            e = cudaMemsetAsync(buf, 0, bytes, st);
+            if (e != cudaSuccess) return e;
+            P.stag = static_cast<double *>(buf);
+            P.stag_pitch = pitch;
+            P.stag_copy = copy / 4 * 4;
+            e = deposit_global_pass(ndim, shape, P, rows, gate, sm_count, st);
+            cudaError_t e2 = cudaFreeAsync(buf, st);
+            return e != cudaSuccess ? e : e2;
+        }
         return deposit_global_pass(ndim, shape, P, rows, gate, sm_count, st);
     }
     for (int s = 0; s < passes; ++s) {

@@ -23,7 +23,8 @@
 namespace ptg {
 
 constexpr int kRT = 256;      // threads per CTA
-constexpr int kRK = 4;        // consecutive particles per thread
+constexpr int kRK = 4;        // consecutive particles per load batch
+constexpr int kRB = 2;        // batches per thread between two warp-level merges (8 consecutive particles)
 
 __device__ __forceinline__ void ld_stream_v2(const double *p, double &a, double &b) {
     unsigned long long pol;
@@ -66,73 +67,84 @@ __global__ void __launch_bounds__(kRT) k_deposit_runs(const DepositParams P, con
     };
 
     // contiguous span per CTA so that concurrently running CTAs work on different grid regions
-    const int64_t per_cta = ((P.n + gridDim.x - 1) / gridDim.x + kRT * kRK - 1) / (kRT * kRK) * (kRT * kRK);
+    const int64_t per_cta = ((P.n + gridDim.x - 1) / gridDim.x + kRT * kRK * kRB - 1) / (kRT * kRK * kRB) * (kRT * kRK * kRB);
     const int64_t begin = (int64_t)blockIdx.x * per_cta;
     const int64_t end = begin + per_cta < P.n ? begin + per_cta : P.n;
 
-    for (int64_t c0 = begin; c0 < end; c0 += kRT * kRK) {
-        const int64_t i0 = c0 + (int64_t)threadIdx.x * kRK;
-        double x[kRK], y[kRK], z[kRK], w[kRK];
-        const bool full = i0 + kRK <= end;
-        if (full) {
-            load_k<VEC>(P.p[0], P.stride[0], i0, x);
-            if (ND >= 2) load_k<VEC>(P.p[1], P.stride[1], i0, y);
-            if (ND >= 3) load_k<VEC>(P.p[2], P.stride[2], i0, z);
-            if (W) load_k<VEC>(P.p[3], P.stride[3], i0, w);
-        } else {
-#pragma unroll
-            for (int j = 0; j < kRK; ++j) {
-                const bool in = i0 + j < end;
-                x[j] = in ? P.p[0][(i0 + j) * P.stride[0]] : 0.0;
-                if (ND >= 2) y[j] = in ? P.p[1][(i0 + j) * P.stride[1]] : 0.0;
-                if (ND >= 3) z[j] = in ? P.p[2][(i0 + j) * P.stride[2]] : 0.0;
-                if (W) w[j] = in ? P.p[3][(i0 + j) * P.stride[3]] : 0.0;
-            }
-        }
+    constexpr int PER = kRK * kRB;         // consecutive particles per thread between two warp merges
+    for (int64_t c0 = begin; c0 < end; c0 += (int64_t)kRT * PER) {
+        const int64_t t0 = c0 + (int64_t)threadIdx.x * PER;
         int cur = -1;                 // base cell of the open run, -1 = none
         double acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-#pragma unroll
-        for (int j = 0; j < kRK; ++j) {
-            int b[3] = {0, 0, 0};
-            double wx[NW], wy[NW], wz[NW];
-            bool ok = i0 + j < end;
-            if constexpr (S == 0) {
-                ok = ngp_axis(x[j], P.lo[0], P.inv[0], P.fbins[0], b[0]) && ok;
-                if (ND >= 2) ok = ngp_axis(y[j], P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
-                if (ND >= 3) ok = ngp_axis(z[j], P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
-                wx[0] = wy[0] = wz[0] = 1.0;
+
+        double x[kRK], y[kRK], z[kRK], w[kRK];
+        auto load_batch = [&](int64_t i0) {
+            if (i0 + kRK <= end) {
+                load_k<VEC>(P.p[0], P.stride[0], i0, x);
+                if (ND >= 2) load_k<VEC>(P.p[1], P.stride[1], i0, y);
+                if (ND >= 3) load_k<VEC>(P.p[2], P.stride[2], i0, z);
+                if (W) load_k<VEC>(P.p[3], P.stride[3], i0, w);
             } else {
-                double (&rx)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wx);
-                double (&ry)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wy);
-                double (&rz)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wz);
-                ok = shape_axis<SS, false>(x[j], P.lo[0], P.inv[0], P.fbins_p1[0], b[0], rx) && ok;
-                if (ND >= 2) ok = shape_axis<SS, true>(y[j], P.lo[1], P.inv[1], P.fbins_p1[1], b[1], ry) && ok;
-                if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z[j], P.lo[2], P.inv[2], P.fbins_p1[2], b[2], rz) && ok;
+#pragma unroll
+                for (int j = 0; j < kRK; ++j) {
+                    const bool in = i0 + j < end;
+                    x[j] = in ? P.p[0][(i0 + j) * P.stride[0]] : 0.0;
+                    if (ND >= 2) y[j] = in ? P.p[1][(i0 + j) * P.stride[1]] : 0.0;
+                    if (ND >= 3) z[j] = in ? P.p[2][(i0 + j) * P.stride[2]] : 0.0;
+                    if (W) w[j] = in ? P.p[3][(i0 + j) * P.stride[3]] : 0.0;
+                }
             }
-            if (!ok) continue;
-            const int key = (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2];      // dims beyond ndim are 1
-            const bool same = key == cur;
-            if (!same && cur >= 0) commit(cur, acc);
-            cur = key;
+        };
+#pragma unroll 1
+        for (int bt = 0; bt < kRB; ++bt) {
+            const int64_t i0 = t0 + bt * kRK;
+            load_batch(i0);
 #pragma unroll
-            for (int a = 0; a < NA; ++a)
+            for (int j = 0; j < kRK; ++j) {
+                int b[3] = {0, 0, 0};
+                double wx[NW], wy[NW], wz[NW];
+                bool ok = i0 + j < end;
+                if constexpr (S == 0) {
+                    ok = ngp_axis(x[j], P.lo[0], P.inv[0], P.fbins[0], b[0]) && ok;
+                    if (ND >= 2) ok = ngp_axis(y[j], P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
+                    if (ND >= 3) ok = ngp_axis(z[j], P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
+                    wx[0] = wy[0] = wz[0] = 1.0;
+                } else {
+                    double (&rx)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wx);
+                    double (&ry)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wy);
+                    double (&rz)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wz);
+                    ok = shape_axis<SS, false>(x[j], P.lo[0], P.inv[0], P.fbins_p1[0], b[0], rx) && ok;
+                    if (ND >= 2) ok = shape_axis<SS, true>(y[j], P.lo[1], P.inv[1], P.fbins_p1[1], b[1], ry) && ok;
+                    if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z[j], P.lo[2], P.inv[2], P.fbins_p1[2], b[2], rz) && ok;
+                }
+                if (!ok) continue;
+                const int key = (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2];      // dims beyond ndim are 1
+                if (key != cur) {            // rare on cell-ordered input: close the run, open a new one
+                    if (cur >= 0) commit(cur, acc);
+                    cur = key;
 #pragma unroll
-                for (int c = 0; c < NC; ++c)
+                    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+                }
 #pragma unroll
-                    for (int d = 0; d < NDD; ++d) {
-                        double v;
-                        if (S == 0) v = W ? w[j] : 1.0;
-                        else if (ND == 1) v = W ? __dmul_rn(wx[a], w[j]) : wx[a];
-                        else {
-                            v = __dmul_rn(wx[a], wy[c]);
-                            if (ND == 3) v = __dmul_rn(v, wz[d]);
-                            if (W) v = __dmul_rn(v, w[j]);
+                for (int a = 0; a < NA; ++a)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+#pragma unroll
+                        for (int d = 0; d < NDD; ++d) {
+                            double v;
+                            if (S == 0) v = W ? w[j] : 1.0;
+                            else if (ND == 1) v = W ? __dmul_rn(wx[a], w[j]) : wx[a];
+                            else {
+                                v = __dmul_rn(wx[a], wy[c]);
+                                if (ND == 3) v = __dmul_rn(v, wz[d]);
+                                if (W) v = __dmul_rn(v, w[j]);
+                            }
+                            const int k = (a * NC + c) * NDD + d;
+                            acc[k] = __dadd_rn(acc[k], v);
                         }
-                        const int k = (a * NC + c) * NDD + d;
-                        acc[k] = same ? __dadd_rn(acc[k], v) : v;
-                    }
+            }
         }
         // merge the runs still open at the end of each lane's K particles across the warp
         const int key = cur >= 0 ? cur : -1 - lane;
@@ -169,7 +181,7 @@ static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, i
         if (P.stride[k] != 1 || (reinterpret_cast<uintptr_t>(P.p[k]) & 15u)) vec = false;
     }
     (void)nd_arrays;
-    int64_t want = (P.n + (int64_t)kRT * kRK - 1) / ((int64_t)kRT * kRK);
+    int64_t want = (P.n + (int64_t)kRT * kRK * kRB - 1) / ((int64_t)kRT * kRK * kRB);
     int64_t cap = (int64_t)sm_count * 4;
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;

@@ -109,6 +109,13 @@ struct DepositParams {
     // slab pass (methods GLOBAL / ROWS on grids larger than L2): only particles whose stencil base
     // cell on axis 0 lies in [slab_lo, slab_hi) are deposited by this launch
     int slab_lo, slab_hi;
+    // staggered staging grid of method ROWS (null = deposit straight into `grid`): two copies of
+    // the grid with rows padded to `stag_pitch` doubles (a multiple of 4, 32-byte aligned base);
+    // copy 1 stores column j at j + 2.  A stencil row of 2 or 3 cells is sent to the copy in
+    // which it does not straddle a 32-byte sector, so every row costs exactly one L2 sector-RED.
+    double *stag;
+    int stag_pitch;
+    int64_t stag_copy;      // distance between the two copies, in doubles
 };
 
 // Streaming 8-byte load: read-only path, do not allocate in L1 and mark the line evict-first
@@ -116,6 +123,10 @@ struct DepositParams {
 // hit).  ptxas folds the policy into the load's descriptor, it costs no instruction.
 __device__ __forceinline__ double ld_stream(const double *p) {
     double v;
+#ifdef PTG_NO_EVICT_FIRST
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+#endif
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
