@@ -140,7 +140,6 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
     double *stage = stage_all + warp * 32 * C::PS;
     const int g = lane / C::G, j = lane % C::G;
 
-    const int64_t nthreads = (int64_t)gridDim.x * kThreads;
     const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
     const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2], sw = P.stride[3];
     // geometry of the array the reductions go to: the padded grid itself, or the staggered staging grid
@@ -149,14 +148,18 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
     const int slab_stride = ND == 3 ? P.dims[1] * pitch : 0;
     double *const target = STAG ? P.stag : P.grid;
 
-    // warp-uniform trip count so that the warp-level exchanges stay convergent
-    const int64_t first = (int64_t)blockIdx.x * kThreads + warp * 32;
-    for (int64_t i0 = first; i0 < P.n; i0 += nthreads) {
+    // Every CTA owns a contiguous span of the particle arrays: on ordered input the CTAs then work
+    // on different parts of the grid at any moment instead of all hammering the same few rows.
+    // (warp-uniform trip count so that the warp-level exchanges stay convergent)
+    const int64_t span = ((P.n + gridDim.x - 1) / gridDim.x + kThreads - 1) / kThreads * kThreads;
+    const int64_t begin = (int64_t)blockIdx.x * span;
+    const int64_t end = begin + span < P.n ? begin + span : P.n;
+    for (int64_t i0 = begin + warp * 32; i0 < end; i0 += kThreads) {
         const int64_t i = i0 + lane;
         double wx[NW], wy[NW], wz[NW];
         int bx = 0, by = 0, bz = 0;
         double w = 1.0;
-        bool ok = i < P.n;
+        bool ok = i < end;
         if (ok) {
             const double x = ld_stream(px + i * sx);
             const double y = ND >= 2 ? ld_stream(py + i * sy) : 0.0;
