@@ -68,6 +68,9 @@ extern "C" {
 #define PTG_METHOD_SORTED    0x40u  /* deterministic: sort by cell + segmented reduce, no atomics  */
 #define PTG_METHOD_RUNS      0x50u  /* cell-ordered input: run-length accumulation in registers,
                                        one reduction per run instead of one per particle          */
+#define PTG_METHOD_RUNS_WIDE 0x60u  /* RUNS with a register window one cell wider per axis: keeps
+                                       runs alive when neighbours' base cells differ by one (odd
+                                       shapes on cell-ordered input); (S+2)^ndim <= 27 only        */
 
 /* ---- introspection ------------------------------------------------------------- */
 int         ptg_abi_version(void);

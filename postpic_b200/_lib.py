@@ -24,8 +24,9 @@ METHOD_ROWS = 0x20
 METHOD_TILED = 0x30
 METHOD_SORTED = 0x40
 METHOD_RUNS = 0x50
+METHOD_RUNS_WIDE = 0x60
 METHODS = {None: METHOD_AUTO, 'auto': METHOD_AUTO, 'global': METHOD_GLOBAL, 'rows': METHOD_ROWS,
-           'tiled': METHOD_TILED, 'sorted': METHOD_SORTED, 'runs': METHOD_RUNS}
+           'tiled': METHOD_TILED, 'sorted': METHOD_SORTED, 'runs': METHOD_RUNS, 'runs_wide': METHOD_RUNS_WIDE}
 
 
 class PtgError(RuntimeError):

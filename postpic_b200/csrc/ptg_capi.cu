@@ -183,13 +183,20 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
             const bool force = method == PTG_METHOD_TILED;
             PTG_CUDA(ptg::deposit_tiled(ndim, shape, P, cfg, force, d->sm_count, st));
             if (!force) {
-                PTG_CUDA(ptg::deposit_runs(ndim, shape, P, cfg, d->sm_count, st));
+                PTG_CUDA(ptg::deposit_runs(ndim, shape, P, cfg, false, d->sm_count, st));
+                if (ptg::runs_wide_available(ndim, shape))
+                    PTG_CUDA(ptg::deposit_runs(ndim, shape, P, cfg, true, d->sm_count, st));
                 PTG_CUDA(ptg::deposit_global(ndim, shape, P, shape > 0, cfg, d->sm_count, st));
             }
             break;
         }
         case PTG_METHOD_RUNS:
-            PTG_CUDA(ptg::deposit_runs(ndim, shape, P, nullptr, d->sm_count, st));
+            PTG_CUDA(ptg::deposit_runs(ndim, shape, P, nullptr, false, d->sm_count, st));
+            break;
+        case PTG_METHOD_RUNS_WIDE:
+            if (!ptg::runs_wide_available(ndim, shape))
+                return fail(PTG_EUNSUPPORTED, "method RUNS_WIDE has no instance for ndim=%d shape=%d", ndim, shape);
+            PTG_CUDA(ptg::deposit_runs(ndim, shape, P, nullptr, true, d->sm_count, st));
             break;
         case PTG_METHOD_SORTED: {
             if (n <= 0) break;

@@ -45,25 +45,33 @@ __device__ __forceinline__ void load_k(const double *base, int64_t stride, int64
     }
 }
 
-template <int ND, int S, bool W, bool VEC>
+template <int ND, int S, bool W, bool VEC, int WD>
 __global__ void __launch_bounds__(kRT) k_deposit_runs(const DepositParams P, const TileConfig *gate) {
-    if (gate != nullptr && gate->mode != kModeRuns) return;
+    if (gate != nullptr && gate->mode != (WD ? kModeRunsWide : kModeRuns)) return;
     constexpr int NW = StencilWidth<S>::value;
     constexpr int SS = S == 0 ? 1 : S;
-    constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
-    constexpr int NV = NA * NC * NDD;
+    // register window of the open run: the stencil of its first particle, widened by WD cells per
+    // axis so that neighbours whose base cell is one further along any axis still fit
+    constexpr int MW = NW + WD;
+    constexpr int MA = MW, MC = ND >= 2 ? MW : 1, MD = ND >= 3 ? MW : 1;
+    constexpr int MV = MA * MC * MD;
     const int lane = threadIdx.x & 31;
     const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
 
-    auto commit = [&](int key, const double (&acc)[NV]) {
-        // key = padded linear index of the base cell
+    auto commit = [&](int key, const double (&acc)[MV]) {
+        // key = padded linear index of the window's first cell.  Exact zeros are skipped: they
+        // carry nothing, and the outermost cells of a widened window may lie beyond the grid
+        // (they can only ever hold zero there).
         double *g = P.grid + key;
 #pragma unroll
-        for (int a = 0; a < NA; ++a)
+        for (int a = 0; a < MA; ++a)
 #pragma unroll
-            for (int c = 0; c < NC; ++c)
+            for (int c = 0; c < MC; ++c)
 #pragma unroll
-                for (int d = 0; d < NDD; ++d) red_add(g + (a * g1 + c) * g2 + d, acc[(a * NC + c) * NDD + d]);
+                for (int d = 0; d < MD; ++d) {
+                    const double v = acc[(a * MC + c) * MD + d];
+                    if (!WD || v != 0.0) red_add(g + (a * g1 + c) * g2 + d, v);
+                }
     };
 
     // contiguous span per CTA so that concurrently running CTAs work on different grid regions
@@ -74,10 +82,11 @@ __global__ void __launch_bounds__(kRT) k_deposit_runs(const DepositParams P, con
     constexpr int PER = kRK * kRB;         // consecutive particles per thread between two warp merges
     for (int64_t c0 = begin; c0 < end; c0 += (int64_t)kRT * PER) {
         const int64_t t0 = c0 + (int64_t)threadIdx.x * PER;
-        int cur = -1;                 // base cell of the open run, -1 = none
-        double acc[NV];
+        int cur = -1;                 // first cell of the open run's window (linear), -1 = none
+        int ab[3] = {0, 0, 0};        // the same per axis
+        double acc[MV];
 #pragma unroll
-        for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+        for (int k = 0; k < MV; ++k) acc[k] = 0.0;
 
         double x[kRK], y[kRK], z[kRK], w[kRK];
         auto load_batch = [&](int64_t i0) {
@@ -120,33 +129,67 @@ __global__ void __launch_bounds__(kRT) k_deposit_runs(const DepositParams P, con
                     if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z[j], P.lo[2], P.inv[2], P.fbins_p1[2], b[2], rz) && ok;
                 }
                 if (!ok) continue;
-                const int key = (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2];      // dims beyond ndim are 1
-                if (key != cur) {            // rare on cell-ordered input: close the run, open a new one
-                    if (cur >= 0) commit(cur, acc);
-                    cur = key;
+                const double wj = W ? w[j] : 1.0;
+                if (WD && W && !(fabs(wj) <= 1.79769313486231570e308)) {
+                    // NaN / inf weight: 0 * w would poison the widened cells -> deposit this particle alone
 #pragma unroll
-                    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
+                    for (int a = 0; a < NW; ++a)
+#pragma unroll
+                        for (int c = 0; c < (ND >= 2 ? NW : 1); ++c)
+#pragma unroll
+                            for (int d = 0; d < (ND >= 3 ? NW : 1); ++d) {
+                                double v = wx[a];
+                                if (ND >= 2) v = __dmul_rn(v, wy[c]);
+                                if (ND >= 3) v = __dmul_rn(v, wz[d]);
+                                red_add(P.grid + (((int64_t)(b[0] + a)) * g1 + (b[1] + c)) * g2 + (b[2] + d), __dmul_rn(v, wj));
+                            }
+                    continue;
+                }
+                bool fits = cur >= 0;
+#pragma unroll
+                for (int a = 0; a < ND; ++a) fits = fits && (unsigned)(b[a] - ab[a]) <= (unsigned)WD;
+                if (!fits) {                 // rare on cell-ordered input: close the run, open a new one
+                    if (cur >= 0) commit(cur, acc);
+                    cur = (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2];      // dims beyond ndim are 1
+#pragma unroll
+                    for (int a = 0; a < 3; ++a) ab[a] = b[a];
+#pragma unroll
+                    for (int k = 0; k < MV; ++k) acc[k] = 0.0;
+                }
+                // stencil weights placed at this particle's offset (0 or 1) inside the window
+                double sx[MW], sy[MW], sz[MW];
+                if (WD) {
+                    const bool ox = b[0] != ab[0], oy = b[1] != ab[1], oz = b[2] != ab[2];
+#pragma unroll
+                    for (int i = 0; i < MW; ++i) {
+                        sx[i] = ox ? (i >= 1 ? wx[i - 1] : 0.0) : (i < NW ? wx[i] : 0.0);
+                        sy[i] = oy ? (i >= 1 ? wy[i - 1] : 0.0) : (i < NW ? wy[i] : 0.0);
+                        sz[i] = oz ? (i >= 1 ? wz[i - 1] : 0.0) : (i < NW ? wz[i] : 0.0);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < MW; ++i) { sx[i] = wx[i]; sy[i] = wy[i]; sz[i] = wz[i]; }
                 }
 #pragma unroll
-                for (int a = 0; a < NA; ++a)
+                for (int a = 0; a < MA; ++a)
 #pragma unroll
-                    for (int c = 0; c < NC; ++c)
+                    for (int c = 0; c < MC; ++c)
 #pragma unroll
-                        for (int d = 0; d < NDD; ++d) {
+                        for (int d = 0; d < MD; ++d) {
                             double v;
-                            if (S == 0) v = W ? w[j] : 1.0;
-                            else if (ND == 1) v = W ? __dmul_rn(wx[a], w[j]) : wx[a];
+                            if (S == 0 && !WD) v = wj;
+                            else if (ND == 1) v = W ? __dmul_rn(sx[a], wj) : sx[a];
                             else {
-                                v = __dmul_rn(wx[a], wy[c]);
-                                if (ND == 3) v = __dmul_rn(v, wz[d]);
-                                if (W) v = __dmul_rn(v, w[j]);
+                                v = __dmul_rn(sx[a], sy[c]);
+                                if (ND == 3) v = __dmul_rn(v, sz[d]);
+                                if (W) v = __dmul_rn(v, wj);
                             }
-                            const int k = (a * NC + c) * NDD + d;
+                            const int k = (a * MC + c) * MD + d;
                             acc[k] = __dadd_rn(acc[k], v);
                         }
             }
         }
-        // merge the runs still open at the end of each lane's K particles across the warp
+        // merge the runs still open at the end of each lane's particles across the warp
         const int key = cur >= 0 ? cur : -1 - lane;
         const int prev = __shfl_up_sync(0xffffffffu, key, 1);
         const bool head = lane == 0 || prev != key;
@@ -159,7 +202,7 @@ __global__ void __launch_bounds__(kRT) k_deposit_runs(const DepositParams P, con
             for (int dd = 1; dd < 32; dd <<= 1) {
                 const bool take = lane + dd < next_head;
 #pragma unroll
-                for (int k = 0; k < NV; ++k) {
+                for (int k = 0; k < MV; ++k) {
                     const double o = __shfl_down_sync(0xffffffffu, acc[k], dd);
                     if (take) acc[k] = __dadd_rn(acc[k], o);
                 }
@@ -170,47 +213,65 @@ __global__ void __launch_bounds__(kRT) k_deposit_runs(const DepositParams P, con
     }
 }
 
+// widened windows are compiled where they fit the register file: (S+2)^ndim <= 27 accumulators
+template <int ND, int S> struct WideOk {
+    static constexpr int MW = StencilWidth<S>::value + 1;
+    static constexpr bool value = (ND == 1 ? MW : ND == 2 ? MW * MW : MW * MW * MW) <= 27;
+};
+
 template <int ND, int S, bool W>
-static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, int sm_count, cudaStream_t st) {
+static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, bool wide, int sm_count, cudaStream_t st) {
     if (P.n <= 0) return cudaSuccess;
     bool vec = true;
-    const int nd_arrays = ND + (W ? 1 : 0);
     for (int k = 0; k < 4; ++k) {
         const bool used = k < ND || (k == 3 && W);
         if (!used) continue;
         if (P.stride[k] != 1 || (reinterpret_cast<uintptr_t>(P.p[k]) & 15u)) vec = false;
     }
-    (void)nd_arrays;
     int64_t want = (P.n + (int64_t)kRT * kRK * kRB - 1) / ((int64_t)kRT * kRK * kRB);
     int64_t cap = (int64_t)sm_count * 4;
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
-    if (vec) k_deposit_runs<ND, S, W, true><<<blocks, kRT, 0, st>>>(P, gate);
-    else k_deposit_runs<ND, S, W, false><<<blocks, kRT, 0, st>>>(P, gate);
+    if (wide) {
+        if constexpr (WideOk<ND, S>::value) {
+            if (vec) k_deposit_runs<ND, S, W, true, 1><<<blocks, kRT, 0, st>>>(P, gate);
+            else k_deposit_runs<ND, S, W, false, 1><<<blocks, kRT, 0, st>>>(P, gate);
+        }
+        return cudaGetLastError();      // (no widened instance for this stencil: nothing launched)
+    }
+    if (vec) k_deposit_runs<ND, S, W, true, 0><<<blocks, kRT, 0, st>>>(P, gate);
+    else k_deposit_runs<ND, S, W, false, 0><<<blocks, kRT, 0, st>>>(P, gate);
     return cudaGetLastError();
 }
 
 template <int ND, int S>
-static cudaError_t runs_w(const DepositParams &P, const TileConfig *gate, int sm, cudaStream_t st) {
-    return P.p[3] ? launch_runs<ND, S, true>(P, gate, sm, st) : launch_runs<ND, S, false>(P, gate, sm, st);
+static cudaError_t runs_w(const DepositParams &P, const TileConfig *gate, bool wide, int sm, cudaStream_t st) {
+    return P.p[3] ? launch_runs<ND, S, true>(P, gate, wide, sm, st) : launch_runs<ND, S, false>(P, gate, wide, sm, st);
 }
 
 template <int ND>
-static cudaError_t runs_s(int shape, const DepositParams &P, const TileConfig *gate, int sm, cudaStream_t st) {
+static cudaError_t runs_s(int shape, const DepositParams &P, const TileConfig *gate, bool wide, int sm, cudaStream_t st) {
     switch (shape) {
-        case 0: return runs_w<ND, 0>(P, gate, sm, st);
-        case 1: return runs_w<ND, 1>(P, gate, sm, st);
-        case 2: return runs_w<ND, 2>(P, gate, sm, st);
-        default: return runs_w<ND, 3>(P, gate, sm, st);
+        case 0: return runs_w<ND, 0>(P, gate, wide, sm, st);
+        case 1: return runs_w<ND, 1>(P, gate, wide, sm, st);
+        case 2: return runs_w<ND, 2>(P, gate, wide, sm, st);
+        default: return runs_w<ND, 3>(P, gate, wide, sm, st);
     }
 }
 
-cudaError_t deposit_runs(int ndim, int shape, const DepositParams &P, const TileConfig *gate, int sm_count,
+bool runs_wide_available(int ndim, int shape) {
+    const int mw = (shape == 0 ? 1 : shape + 1) + 1;
+    int mv = 1;
+    for (int a = 0; a < ndim; ++a) mv *= mw;
+    return mv <= 27;
+}
+
+cudaError_t deposit_runs(int ndim, int shape, const DepositParams &P, const TileConfig *gate, bool wide, int sm_count,
                          cudaStream_t st) {
     switch (ndim) {
-        case 1: return runs_s<1>(shape, P, gate, sm_count, st);
-        case 2: return runs_s<2>(shape, P, gate, sm_count, st);
-        default: return runs_s<3>(shape, P, gate, sm_count, st);
+        case 1: return runs_s<1>(shape, P, gate, wide, sm_count, st);
+        case 2: return runs_s<2>(shape, P, gate, wide, sm_count, st);
+        default: return runs_s<3>(shape, P, gate, wide, sm_count, st);
     }
 }
 

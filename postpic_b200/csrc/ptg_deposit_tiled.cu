@@ -73,7 +73,7 @@ __device__ __forceinline__ bool base_cells(const DepositParams &P, double x, dou
 // probe: pick the window shape
 // ---------------------------------------------------------------------------------
 template <int ND, int S>
-__global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig *cfg, int force) {
+__global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig *cfg, int force, int wide_ok) {
     __shared__ long long scratch[34];
     __shared__ bool s_last;
     constexpr int NW = StencilWidth<S>::value;
@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
     {
         TileConfig::Part part;
         part.mad[0] = part.mad[1] = part.mad[2] = 0.f;
-        part.cnt = part.eq_pairs = part.all_pairs = 0;
-        part.pad[0] = part.pad[1] = 0;
+        part.cnt = part.eq_pairs = part.all_pairs = part.near_pairs = 0;
+        part.pad = 0;
         if (P.n >= 2 * kTT) {
             const int64_t start = (P.n - kTT) / (kProbeBlocks - 1) * blockIdx.x;
             const int64_t i = start + threadIdx.x;
@@ -100,6 +100,14 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
                 const bool pair = (threadIdx.x & 31) != 0 && key >= 0 && prev >= 0;
                 part.eq_pairs = (int)block_sum(pair && key == prev ? 1 : 0, scratch);
                 part.all_pairs = (int)block_sum(pair ? 1 : 0, scratch);
+                // neighbours that a register window one cell wider per axis would still hold
+                // (either particle of the pair may be the one further along)
+                bool near = pair;
+                for (int a = 0; a < ND; ++a) {
+                    const int pb = __shfl_up_sync(0xffffffffu, b[a], 1);
+                    near = near && (b[a] - pb) >= -1 && (b[a] - pb) <= 1;
+                }
+                part.near_pairs = (int)block_sum(near ? 1 : 0, scratch);
                 for (int a = 0; a < ND; ++a) {
                     const long long sum = block_sum(ok ? b[a] : 0, scratch);
                     const long long mean = sum / cnt;
@@ -120,7 +128,7 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
     }
     double mad_sum[3] = {0, 0, 0};
     int blocks_used = 0;
-    long long eq_pairs = 0, all_pairs = 0;
+    long long eq_pairs = 0, all_pairs = 0, near_pairs = 0;
     for (int blk = 0; blk < (int)gridDim.x; ++blk) {
         const volatile TileConfig::Part *q = &cfg->part[blk];
         if (q->cnt < 32) continue;
@@ -128,12 +136,14 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
         for (int a = 0; a < ND; ++a) mad_sum[a] += q->mad[a];
         eq_pairs += q->eq_pairs;
         all_pairs += q->all_pairs;
+        near_pairs += q->near_pairs;
     }
     if (threadIdx.x != 0) return;
-    struct { int mode; int ext[3]; float est_hit; float run_frac; } c;
+    struct { int mode; int ext[3]; float est_hit; float run_frac; float near_frac; } c;
     c.mode = kModeRows;
     c.est_hit = 0.f;
     c.run_frac = all_pairs > 0 ? (float)((double)eq_pairs / (double)all_pairs) : 0.f;
+    c.near_frac = all_pairs > 0 ? (float)((double)near_pairs / (double)all_pairs) : 0.f;
     c.ext[0] = c.ext[1] = c.ext[2] = 1;
     if (blocks_used > 0 || force) {
         double need[3] = {1, 1, 1}, prod = 1;
@@ -180,10 +190,12 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
     // long runs of equal base cells: register run-length accumulation beats the tile
     // (break-even is an average run of ~2.5 particles)
     if (!force && c.run_frac >= 0.6f) c.mode = kModeRuns;
+    else if (!force && c.near_frac >= 0.75f && wide_ok) c.mode = kModeRunsWide;
     cfg->mode = c.mode;
     for (int a = 0; a < 3; ++a) cfg->ext[a] = c.ext[a];
     cfg->est_hit = c.est_hit;
     cfg->run_frac = c.run_frac;
+    cfg->near_frac = c.near_frac;
     cfg->ticket = 0;                      // ready for the next call that gets this ring entry
 }
 
@@ -430,7 +442,7 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
     // per-device attribute, cheap to set: done on every launch so that any device works
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_probe<ND, S><<<kProbeBlocks, kTT, 0, st>>>(P, cfg, force);
+    k_probe<ND, S><<<kProbeBlocks, kTT, 0, st>>>(P, cfg, force, runs_wide_available(ND, S) ? 1 : 0);
     kern<<<sm_count, TT, smem, st>>>(P, cfg);
     return cudaGetLastError();
 }

@@ -9,7 +9,7 @@ namespace ptg {
 
 // Decision record of the probe kernel (device memory): whether a shared-memory tile pays off
 // for this launch and the window extents it chose.
-enum : int { kModeRows = 0, kModeTiled = 1, kModeRuns = 2 };
+enum : int { kModeRows = 0, kModeTiled = 1, kModeRuns = 2, kModeRunsWide = 3 };
 
 constexpr int kProbeBlocks = 16;
 
@@ -18,10 +18,11 @@ struct TileConfig {
     int ext[3];        // tile window extents chosen for kModeTiled
     float est_hit;     // estimated fraction of particles that fall into such a window
     float run_frac;    // fraction of consecutive particle pairs with equal stencil base cell
+    float near_frac;   // ... whose base cells differ by at most one cell forward on every axis
     unsigned ticket;   // probe CTAs that have finished (reset to 0 by the last one)
     int pad;
     // per-probe-CTA partial statistics
-    struct Part { float mad[3]; int cnt; int eq_pairs; int all_pairs; int pad[2]; } part[kProbeBlocks];
+    struct Part { float mad[3]; int cnt; int eq_pairs; int all_pairs; int near_pairs; int pad; } part[kProbeBlocks];
 };
 
 // ptg_deposit_global.cu -- `gate` (nullable): the kernels return at once unless gate->mode is
@@ -34,8 +35,10 @@ cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfi
                           cudaStream_t st);
 
 // ptg_deposit_runs.cu -- run-length accumulation in registers for cell-ordered input
-cudaError_t deposit_runs(int ndim, int shape, const DepositParams &P, const TileConfig *gate, int sm_count,
+// (`wide`: the variant whose register window is one cell wider per axis, mode kModeRunsWide)
+cudaError_t deposit_runs(int ndim, int shape, const DepositParams &P, const TileConfig *gate, bool wide, int sm_count,
                          cudaStream_t st);
+bool runs_wide_available(int ndim, int shape);
 
 // ptg_deposit_sorted.cu -- deterministic sort-by-cell + segmented reduce; needs a workspace of
 // sorted_workspace_bytes(n, cells) bytes
