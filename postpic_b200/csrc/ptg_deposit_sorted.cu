@@ -66,27 +66,41 @@ __global__ void __launch_bounds__(256) k_cell_offsets(const uint32_t *keys, int6
     }
 }
 
-template <int ND, int S, bool W>
+constexpr uint32_t kLongSegment = 2048;     // segments longer than this get a whole CTA instead of a warp
+
+// LONG = false: one warp per base cell, segments of up to kLongSegment particles.
+// LONG = true : one CTA (8 warps) per base cell for the longer segments of clustered input: the
+//               segment is cut into 8 equal contiguous parts, one per warp, and the 8 partial
+//               totals are added in warp order -- still a fixed summation order.
+template <int ND, int S, bool W, bool LONG>
 __global__ void __launch_bounds__(256) k_segment_reduce(const DepositParams P, const uint32_t *idx,
                                                          const uint32_t *off, int cx, int cy, int cz) {
     constexpr int NW = StencilWidth<S>::value;
     constexpr int SS = S == 0 ? 1 : S;
     constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
     constexpr int NV = NA * NC * NDD;
+    __shared__ double s_part[LONG ? 8 * NV : 1];
     // base cells of this colour: b = colour + NW * k, with b + NW <= dims
     const int nx = (P.dims[0] - NW - cx) / NW + 1;
     const int ny = ND >= 2 ? (P.dims[1] - NW - cy) / NW + 1 : 1;
     const int nz = ND >= 3 ? (P.dims[2] - NW - cz) / NW + 1 : 1;
     if (nx <= 0 || ny <= 0 || nz <= 0) return;
     const int64_t ncell = (int64_t)nx * ny * nz;
-    const int lane = threadIdx.x & 31;
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t cc = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); cc < ncell; cc += nwarps) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nworkers = LONG ? (int64_t)gridDim.x : (int64_t)gridDim.x * 8;
+    const int64_t worker = LONG ? (int64_t)blockIdx.x : (int64_t)blockIdx.x * 8 + warp;
+    for (int64_t cc = worker; cc < ncell; cc += nworkers) {
         const int kz = (int)(cc % nz), ky = (int)((cc / nz) % ny), kx = (int)(cc / ((int64_t)nz * ny));
         const int bx = cx + NW * kx, by = cy + NW * ky, bz = cz + NW * kz;
         const uint32_t lin = (uint32_t)((bx * P.dims[1] + by) * P.dims[2] + bz);
-        const uint32_t s0 = off[lin], s1 = off[lin + 1];
-        if (s0 == s1) continue;                                    // warp-uniform
+        uint32_t s0 = off[lin], s1 = off[lin + 1];
+        const uint32_t len = s1 - s0;
+        if (len == 0 || (len > kLongSegment) != LONG) continue;          // warp- (CTA-) uniform
+        if (LONG) {                                                       // this warp's part of the segment
+            const uint32_t part = (len + 7) / 8;
+            s0 = s0 + warp * part;
+            s1 = s0 + part < s1 ? s0 + part : s1;
+        }
         double acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
@@ -130,18 +144,35 @@ __global__ void __launch_bounds__(256) k_segment_reduce(const DepositParams P, c
         for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
             for (int k = 0; k < NV; ++k) acc[k] = __dadd_rn(acc[k], __shfl_xor_sync(0xffffffffu, acc[k], o));
-        if (lane == 0) {
-            const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
-            double *g = P.grid + ((int64_t)bx * g1 + by) * g2 + bz;
+        const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
+        double *g = P.grid + ((int64_t)bx * g1 + by) * g2 + bz;
+        if (!LONG) {
+            if (lane == 0) {
 #pragma unroll
-            for (int a = 0; a < NA; ++a)
+                for (int a = 0; a < NA; ++a)
 #pragma unroll
-                for (int c = 0; c < NC; ++c)
+                    for (int c = 0; c < NC; ++c)
 #pragma unroll
-                    for (int d = 0; d < NDD; ++d) {
-                        double *q = g + (a * g1 + c) * g2 + d;
-                        *q = __dadd_rn(*q, acc[(a * NC + c) * NDD + d]);
-                    }
+                        for (int d = 0; d < NDD; ++d) {
+                            double *q = g + (a * g1 + c) * g2 + d;
+                            *q = __dadd_rn(*q, acc[(a * NC + c) * NDD + d]);
+                        }
+            }
+        } else {
+            __syncthreads();                 // previous cell's partials have been consumed
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) s_part[warp * NV + k] = acc[k];
+            }
+            __syncthreads();
+            if (threadIdx.x < NV) {
+                const int k = threadIdx.x;
+                double t = s_part[k];
+                for (int wv = 1; wv < 8; ++wv) t = __dadd_rn(t, s_part[wv * NV + k]);
+                const int d = k % NDD, c = (k / NDD) % NC, a = k / (NDD * NC);
+                double *q = g + (a * g1 + c) * g2 + d;
+                *q = __dadd_rn(*q, t);
+            }
         }
     }
 }
@@ -201,7 +232,10 @@ static cudaError_t run_sorted(const DepositParams &P, void *ws, size_t ws_bytes,
                 if (ncell <= 0) continue;
                 int64_t wantb = (ncell + 7) / 8;                  // 8 warps per CTA
                 int nb = (int)(wantb < cap * 4 ? wantb : cap * 4);
-                k_segment_reduce<ND, S, W><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
+                k_segment_reduce<ND, S, W, false><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
+                // the long segments of the same colour (clustered input), one CTA each
+                nb = (int)(ncell < cap ? ncell : cap);
+                k_segment_reduce<ND, S, W, true><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
             }
     return cudaGetLastError();
 }
