@@ -164,7 +164,13 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
     fill_params(P, ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid);
     if (flags & PTG_ZERO_GRID)
         PTG_CUDA(cudaMemsetAsync(grid, 0, (size_t)ptg_padded_cells(ndim, shape, bins) * sizeof(double), st));
-    const unsigned method = flags & PTG_METHOD_MASK;
+    unsigned method = flags & PTG_METHOD_MASK;
+    if (method == PTG_METHOD_AUTO && n < (int64_t(1) << 21)) {
+        // small calls are bound by launch latency, not by the GPU: skip the probe and the gated
+        // launches.  A grid that fits the shared-memory tile is privatised, anything else goes
+        // through the L2 reductions.
+        method = ptg_padded_cells(ndim, shape, bins) <= ptg::kTileCells ? PTG_METHOD_TILED : PTG_METHOD_ROWS;
+    }
     switch (method) {
         case PTG_METHOD_GLOBAL:
             PTG_CUDA(ptg::deposit_global(ndim, shape, P, false, nullptr, d->sm_count, st));

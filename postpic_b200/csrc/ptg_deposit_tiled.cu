@@ -27,7 +27,6 @@ constexpr int kTT = 512;                  // probe CTA width
 // CTA width of the tiled kernel by stencil size: small stencils need few registers, so more warps
 // can keep shared-memory atomics in flight (one CTA per SM owns the whole 200 KB tile)
 template <int NV> struct TileThreads { static constexpr int value = NV <= 4 ? 1024 : NV <= 9 ? 768 : 512; };
-constexpr int kTileCells = 25600;         // 200 KB of doubles
 constexpr int kEvalEvery = 4;             // sub-chunks between hit-rate evaluations
 
 // ---------------------------------------------------------------------------------

@@ -12,6 +12,7 @@ namespace ptg {
 enum : int { kModeRows = 0, kModeTiled = 1, kModeRuns = 2, kModeRunsWide = 3 };
 
 constexpr int kProbeBlocks = 16;
+constexpr int kTileCells = 25600;         // doubles in the 200 KB shared-memory tile of method TILED
 
 struct TileConfig {
     int mode;          // which of the kernels launched for an AUTO call does the work
