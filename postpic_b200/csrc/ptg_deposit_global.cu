@@ -113,19 +113,18 @@ __global__ void __launch_bounds__(kThreads) k_deposit_global(const DepositParams
 // ---------------------------------------------------------------------------------
 // method ROWS: sector-coalesced reductions
 // ---------------------------------------------------------------------------------
-// Lanes per row group (next power of two >= NW) and the padded per-particle stride of
-// the staging area, in doubles.  The stride is chosen so that the transposed read is
-// free of shared-memory bank conflicts within a 16-lane phase:
-//   NW = 2 (G = 2): 8 groups x 2 doubles  -> stride == 6 (mod 16) visits 0,6,12,2,8,14,4,10
-//   NW = 3,4 (G = 4): 4 groups x <=4 doubles -> stride == 4 or 12 (mod 16)
+// Lanes per row group (next power of two >= NW) and the layout of the per-warp staging area:
+// value k of the particle held by lane p lives at stage[k * KS + p].  Writes (fixed k, p = lane)
+// are contiguous, hence conflict-free.  The transposed read has lane (g, j) fetch value
+// row*NW + j of particle pg*PPI + g; with KS == 4 (mod 16) for G = 4 -- resp. 8 (mod 16) for
+// G = 2 -- the 16 lanes of a 64-bit phase fall on 16 different bank pairs: (4j + g) resp. (8j + g).
 template <int ND, int S> struct RowsCfg {
     static constexpr int NW = S + 1;
     static constexpr int G = NW == 2 ? 2 : 4;
     static constexpr int ROWS = ND == 1 ? 1 : NW;          // rows per slab
     static constexpr int SLABS = ND == 3 ? NW : 1;
     static constexpr int K = ROWS * NW;                     // doubles staged per particle per slab
-    static constexpr int PS = NW == 2 ? (K <= 6 ? 6 : 22)   // K is 2 or 4
-                                      : (K <= 4 ? 4 : K <= 12 ? 12 : 20);
+    static constexpr int KS = NW == 2 ? 40 : 36;            // stride between consecutive values k
     static constexpr int PPI = 32 / G;                      // particles per RED instruction
     static constexpr int ITERS = ROWS * G;
 };
@@ -135,9 +134,9 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
     if (gate != nullptr && gate->mode != kModeRows) return;
     using C = RowsCfg<ND, S>;
     constexpr int NW = C::NW;
-    __shared__ __align__(16) double stage_all[(kThreads / 32) * 32 * C::PS];
+    __shared__ __align__(16) double stage_all[(kThreads / 32) * C::K * C::KS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *stage = stage_all + warp * 32 * C::PS;
+    double *stage = stage_all + warp * C::K * C::KS;
     const int g = lane / C::G, j = lane % C::G;
 
     const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
@@ -185,17 +184,17 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
 #pragma unroll
         for (int slab = 0; slab < C::SLABS; ++slab) {
             if (ok) {
-                double *mine = stage + lane * C::PS;
+                double *mine = stage + lane;
                 if (ND == 1) {
 #pragma unroll
-                    for (int a = 0; a < NW; ++a) mine[a] = W ? __dmul_rn(wx[a], w) : wx[a];
+                    for (int a = 0; a < NW; ++a) mine[a * C::KS] = W ? __dmul_rn(wx[a], w) : wx[a];
                 } else if (ND == 2) {
 #pragma unroll
                     for (int a = 0; a < NW; ++a)
 #pragma unroll
                         for (int b = 0; b < NW; ++b) {
                             const double c = __dmul_rn(wx[a], wy[b]);
-                            mine[a * NW + b] = W ? __dmul_rn(c, w) : c;
+                            mine[(a * NW + b) * C::KS] = W ? __dmul_rn(c, w) : c;
                         }
                 } else {
 #pragma unroll
@@ -204,7 +203,7 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
 #pragma unroll
                         for (int b = 0; b < NW; ++b) {
                             const double c = __dmul_rn(cxy, wz[b]);
-                            mine[a * NW + b] = W ? __dmul_rn(c, w) : c;
+                            mine[(a * NW + b) * C::KS] = W ? __dmul_rn(c, w) : c;
                         }
                     }
                 }
@@ -216,7 +215,7 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
                 const int p = pg * C::PPI + g;
                 const int l0 = __shfl_sync(0xffffffffu, lin0, p);
                 if (j < NW && l0 >= 0) {
-                    const double v = stage[p * C::PS + row * NW + j];
+                    const double v = stage[(row * NW + j) * C::KS + p];
                     red_add(target + (int64_t)l0 + (int64_t)slab * slab_stride + row * row_stride + j, v);
                 }
             }
