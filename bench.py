@@ -404,7 +404,18 @@ def run_b200_arm(args):
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": n * world / dt * 1e-9, "unit": UNIT, "h2d_bytes_per_step": n * bpp,
+        pageable = None
+        if world == 1:
+            # the same call on ordinary (pageable) numpy arrays, as a postpic user would pass them
+            pg_c = [np.array(c) for c in np_c]
+            pg_w = np.array(np_w)
+            histogramdd(tuple(pg_c), weights=pg_w, range=ranges, bins=list(bins), shape=shape)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                histogramdd(tuple(pg_c), weights=pg_w, range=ranges, bins=list(bins), shape=shape)
+            pageable = n / ((time.perf_counter() - t0) / 3) * 1e-9
+            del pg_c, pg_w
+        e2e = {"value": n * world / dt * 1e-9, "unit": UNIT, "h2d_bytes_per_step": n * bpp, "pageable_value": pageable,
                "d2h_bytes_per_step": plan.cells * 8, "ms_per_step": dt * 1e3, "steps": ksteps,
                "api": "postpic_b200.histogramdd(numpy views of pinned host memory)" if world == 1 else
                       "pinned host -> device copy + postpic_b200.parallel.deposit_sharded + grid D2H"}

@@ -118,6 +118,9 @@ int ptg_zero_f64(double *grid, int64_t count, void *stream);
  * are streamed to the GPU in chunks through a small ring of device buffers so that the
  * PCIe copy of chunk k+1 overlaps the deposit of chunk k; the padded grid is copied
  * back to `grid` (which is overwritten, not accumulated into) before the call returns.
+ * Page-locked unit-stride sources are DMA'd in place; pageable memory and any element
+ * stride (negative and zero included) are gathered into a pinned ring by worker threads
+ * first (PTG_HOST_THREADS overrides their number).
  * Synchronous.  `device` < 0 means the current device.
  */
 int ptg_histogram_host_f64(int ndim, int shape, int64_t n,

@@ -43,11 +43,14 @@ def _host_array(a, name):
     return a
 
 
-def _unit_stride(a):
-    # the C ABI takes positive element strides; anything else becomes one contiguous copy
-    if a.shape[0] <= 1 or a.strides[0] == 8:
-        return a
-    return np.ascontiguousarray(a)
+def _element_stride(a):
+    """(array, stride in doubles) for the C ABI, which gathers strided / reversed host views into its
+    pinned staging ring itself; only byte strides that are not a multiple of 8 need a copy first."""
+    if a.shape[0] <= 1:
+        return np.ascontiguousarray(a), 1
+    if a.strides[0] % 8 == 0:
+        return a, a.strides[0] // 8
+    return np.ascontiguousarray(a), 1
 
 
 def _deposit(coords, names, weights, ranges, bins, shape):
@@ -79,14 +82,18 @@ def _deposit(coords, names, weights, ranges, bins, shape):
         grid = grid_t.cpu().numpy()
     else:
         lib = _lib.load()
-        coords = [_unit_stride(c) for c in coords]
+        pairs = [_element_stride(c) for c in coords]
+        coords = [p[0] for p in pairs]
+        strides = [p[1] for p in pairs] + [1] * (3 - ndim)
+        wstride = 1
         if weights is not None:
-            weights = _unit_stride(weights)
+            weights, wstride = _element_stride(weights)
+        cstrides = (ctypes.c_int64 * 4)(*(strides + [wstride]))
         grid = np.empty(plan.dims, dtype=np.float64)
         ptr = [c.ctypes.data if n else None for c in coords] + [None] * (3 - ndim)
         wptr = weights.ctypes.data if (weights is not None and n) else None
         _lib.check(lib.ptg_histogram_host_f64(
-            ndim, plan.shape, n, ptr[0], ptr[1], ptr[2], wptr, None,
+            ndim, plan.shape, n, ptr[0], ptr[1], ptr[2], wptr, cstrides,
             plan.lo.ctypes.data, plan.inv.ctypes.data, plan.cbins, grid.ctypes.data,
             _lib.METHODS[method], -1 if device_index is None else int(device_index)))
     return grid[plan.interior], plan.edges
