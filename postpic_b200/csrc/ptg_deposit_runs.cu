@@ -24,7 +24,8 @@ namespace ptg {
 
 constexpr int kRT = 256;      // threads per CTA
 constexpr int kRK = 4;        // consecutive particles per load batch
-constexpr int kRB = 2;        // batches per thread between two warp-level merges (8 consecutive particles)
+constexpr int kRB = 2;        // batches per thread between two warp-level merges (8 consecutive particles;
+                              // 16 measured slower: a lane's 128-byte span is then fetched in four visits)
 
 __device__ __forceinline__ void ld_stream_v2(const double *p, double &a, double &b) {
     unsigned long long pol;
@@ -45,8 +46,15 @@ __device__ __forceinline__ void load_k(const double *base, int64_t stride, int64
     }
 }
 
+// resident CTAs per SM asked of ptxas: 4 (64 registers) for register windows of up to 9 cells
+template <int ND, int S, int WD> struct RunsMinBlocks {
+    static constexpr int MW = StencilWidth<S>::value + WD;
+    static constexpr int MV = ND == 1 ? MW : ND == 2 ? MW * MW : MW * MW * MW;
+    static constexpr int value = MV <= 9 ? 4 : MV <= 16 ? 3 : 2;
+};
+
 template <int ND, int S, bool W, bool VEC, int WD>
-__global__ void __launch_bounds__(kRT) k_deposit_runs(const DepositParams P, const TileConfig *gate) {
+__global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposit_runs(const DepositParams P, const TileConfig *gate) {
     if (gate != nullptr && gate->mode != (WD ? kModeRunsWide : kModeRuns)) return;
     constexpr int NW = StencilWidth<S>::value;
     constexpr int SS = S == 0 ? 1 : S;
@@ -109,12 +117,14 @@ __global__ void __launch_bounds__(kRT) k_deposit_runs(const DepositParams P, con
 #pragma unroll 1
         for (int bt = 0; bt < kRB; ++bt) {
             const int64_t i0 = t0 + bt * kRK;
+            if (i0 >= end) break;
             load_batch(i0);
+            const int valid = i0 + kRK <= end ? kRK : (int)(end - i0);      // particles of this batch that exist
 #pragma unroll
             for (int j = 0; j < kRK; ++j) {
                 int b[3] = {0, 0, 0};
                 double wx[NW], wy[NW], wz[NW];
-                bool ok = i0 + j < end;
+                bool ok = j < valid;
                 if constexpr (S == 0) {
                     ok = ngp_axis(x[j], P.lo[0], P.inv[0], P.fbins[0], b[0]) && ok;
                     if (ND >= 2) ok = ngp_axis(y[j], P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
@@ -204,7 +214,9 @@ __global__ void __launch_bounds__(kRT) k_deposit_runs(const DepositParams P, con
 #pragma unroll
                 for (int k = 0; k < MV; ++k) {
                     const double o = __shfl_down_sync(0xffffffffu, acc[k], dd);
-                    if (take) acc[k] = __dadd_rn(acc[k], o);
+                    // predicated add (one @P DADD) instead of the add + two 32-bit selects nvcc emits
+                    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}"
+                        : "+d"(acc[k]) : "d"(o), "r"((int)take));
                 }
             }
             mine = mine && head;
