@@ -13,8 +13,8 @@
 // uncoalesced RED per stencil cell per particle); AUTO selects this method only when
 // the probe kernel saw runs.
 //
-// Particle arrays are read with 16-byte vector loads when contiguous and aligned
-// (every lane reads K consecutive doubles = 2 sectors, a warp 32*K*8 contiguous bytes).
+// Particle arrays are read with 256-bit loads when contiguous and 32-byte aligned (a lane's four
+// consecutive doubles are one sector; a warp reads 1 KB contiguous per array and batch).
 //
 // Replaces the loops of /root/reference/postpic/particles/_particlestogrid.pyx
 // :70-129 (1-D), :181-276 (2-D), :341-463 (3-D).
@@ -27,19 +27,24 @@ constexpr int kRK = 4;        // consecutive particles per load batch
 constexpr int kRB = 2;        // batches per thread between two warp-level merges (8 consecutive particles;
                               // 16 measured slower: a lane's 128-byte span is then fetched in four visits)
 
-__device__ __forceinline__ void ld_stream_v2(const double *p, double &a, double &b) {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
-                 : "=d"(a), "=d"(b) : "l"(p), "l"(pol));
+// 256-bit load (sm_100: LDG.E.NA.EFL2.256): the four consecutive doubles of one lane are exactly one
+// 32-byte sector, fetched once, not allocated in L1 and marked evict-first in L2.
+__device__ __forceinline__ void ld_stream_v4(const double *p, double (&v)[4]) {
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    v[0] = __longlong_as_double((long long)a);
+    v[1] = __longlong_as_double((long long)b);
+    v[2] = __longlong_as_double((long long)c);
+    v[3] = __longlong_as_double((long long)d);
 }
 
 // K consecutive values starting at element i (all K valid)
 template <bool VEC>
 __device__ __forceinline__ void load_k(const double *base, int64_t stride, int64_t i, double (&v)[kRK]) {
     if (VEC) {
-#pragma unroll
-        for (int j = 0; j < kRK; j += 2) ld_stream_v2(base + i + j, v[j], v[j + 1]);
+        static_assert(kRK == 4, "one 256-bit load per batch");
+        ld_stream_v4(base + i, v);
     } else {
 #pragma unroll
         for (int j = 0; j < kRK; ++j) v[j] = __ldg(base + (i + j) * stride);   // L1 keeps the shared sectors
@@ -238,7 +243,7 @@ static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, b
     for (int k = 0; k < 4; ++k) {
         const bool used = k < ND || (k == 3 && W);
         if (!used) continue;
-        if (P.stride[k] != 1 || (reinterpret_cast<uintptr_t>(P.p[k]) & 15u)) vec = false;
+        if (P.stride[k] != 1 || (reinterpret_cast<uintptr_t>(P.p[k]) & 31u)) vec = false;
     }
     int64_t want = (P.n + (int64_t)kRT * kRK * kRB - 1) / ((int64_t)kRT * kRK * kRB);
     int64_t cap = (int64_t)sm_count * 4;
