@@ -364,6 +364,13 @@ def run_b200_arm(args):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
+    probe = None
+    if args.method == "auto" and n >= (1 << 21):
+        try:
+            probe = _lib.last_probe()
+        except Exception:
+            probe = None
+
     # parity spot-check of what was just timed (cheap: mass conservation incl. ghost cells)
     tw = w.sum()
     if world > 1:
@@ -462,7 +469,7 @@ def run_b200_arm(args):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "variants": variants,
             "gpu_launches": args.steps * world * {"auto": 4, "tiled": 2}.get(args.method, 1),
             "clocks": clocks.summary(),
-            "parity": {"mass_conservation_rel_err": mass_err},
+            "parity": {"mass_conservation_rel_err": mass_err}, "auto_probe": probe,
         }
         print(json.dumps(line))
     if world > 1:

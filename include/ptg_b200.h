@@ -136,6 +136,9 @@ int ptg_release(void);
 /* out[i] = the library's division-by-6 of in[i] (device pointers) -- checked bit-for-bit
  * against IEEE division by the tests.                                                   */
 int ptg_selftest_div6(int64_t n, const double *in, double *out, void *stream);
+/* the verdict of the most recent AUTO / TILED probe on the current device (synchronises):
+ * mode 0 = ROWS, 1 = TILED, 2 = RUNS, 3 = RUNS_WIDE; ext[3] = tile window extents.          */
+int ptg_debug_last_probe(int *mode, int *ext, float *est_hit, float *run_frac, float *near_frac);
 
 #ifdef __cplusplus
 }

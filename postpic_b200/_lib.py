@@ -62,6 +62,7 @@ SIGNATURES = {
     "ptg_minmax_host_f64": (_c.c_int, [_I64, _P, _I64, _P, _c.c_int]),
     "ptg_release": (_c.c_int, []),
     "ptg_selftest_div6": (_c.c_int, [_I64, _P, _P, _P]),
+    "ptg_debug_last_probe": (_c.c_int, [_P, _P, _P, _P, _P]),
 }
 
 _lib = None
@@ -111,3 +112,17 @@ def device_info(device=-1):
                               _c.byref(major), _c.byref(minor)))
     return dict(name=name.value.decode(), sm_count=sm.value, l2_bytes=l2.value, hbm_bytes=hbm.value,
                 cc=(major.value, minor.value))
+
+
+PROBE_MODES = {0: 'rows', 1: 'tiled', 2: 'runs', 3: 'runs_wide'}
+
+
+def last_probe():
+    """Verdict of the most recent AUTO / TILED probe on the current device (test / diagnostics hook)."""
+    lib = load()
+    mode = _c.c_int(0)
+    ext = (_c.c_int * 3)()
+    hit, run, near = _c.c_float(0), _c.c_float(0), _c.c_float(0)
+    check(lib.ptg_debug_last_probe(_c.byref(mode), ext, _c.byref(hit), _c.byref(run), _c.byref(near)))
+    return dict(mode=PROBE_MODES.get(mode.value, mode.value), ext=list(ext), est_hit=hit.value,
+                run_frac=run.value, near_frac=near.value)

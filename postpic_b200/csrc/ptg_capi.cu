@@ -595,6 +595,22 @@ int ptg_release(void) {
     return PTG_OK;
 }
 
+int ptg_debug_last_probe(int *mode, int *ext, float *est_hit, float *run_frac, float *near_frac) {
+    DeviceState *d;
+    int rc = current_device_state(&d);
+    if (rc) return rc;
+    if (!d->cfg_ring || d->cfg_next.load() == 0) return fail(PTG_EINVAL, "no AUTO/TILED call has been made on this device yet");
+    ptg::TileConfig c;
+    PTG_CUDA(cudaDeviceSynchronize());
+    PTG_CUDA(cudaMemcpy(&c, d->cfg_ring + ((d->cfg_next.load() - 1) % kCfgRing), sizeof c, cudaMemcpyDeviceToHost));
+    if (mode) *mode = c.mode;
+    if (ext) for (int a = 0; a < 3; ++a) ext[a] = c.ext[a];
+    if (est_hit) *est_hit = c.est_hit;
+    if (run_frac) *run_frac = c.run_frac;
+    if (near_frac) *near_frac = c.near_frac;
+    return PTG_OK;
+}
+
 int ptg_selftest_div6(int64_t n, const double *in, double *out, void *stream) {
     if (n < 0 || (n > 0 && (!in || !out))) return fail(PTG_EINVAL, "ptg_selftest_div6: bad arguments");
     DeviceState *d;

@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
         for (int a = 0; a < ND; ++a) {
             const double mad = blocks_used ? mad_sum[a] / blocks_used : P.dims[a];
             need[a] = 4.0 * mad + NW + 3;
-            if (need[a] > P.dims[a]) need[a] = P.dims[a];
+            // a spread that covers (nearly) the whole axis is the whole axis: the 512-particle sample
+            // of a uniform axis gives 4*MAD within a few per cent of its length
+            if (need[a] > 0.85 * P.dims[a]) need[a] = P.dims[a];
             prod *= need[a];
         }
         double ext[3] = {need[0], need[1], need[2]};

@@ -419,3 +419,34 @@ def test_cell_ordered_input_odd_shapes(nd, shape):
         assert torch.equal(torch.isfinite(got), torch.isfinite(ref)), m
         fin = torch.isfinite(ref)
         assert float((got[fin] - ref[fin]).abs().max()) <= 1e-12 * float(ref[fin].abs().max()), m
+
+
+def test_auto_probe_verdicts():
+    """AUTO's device-side probe picks the method the input order calls for."""
+    import torch
+    from postpic_b200 import device, _lib
+    n = 8_000_000
+    g = torch.Generator(device='cuda').manual_seed(1)
+    x = torch.rand(n, dtype=torch.float64, device='cuda', generator=g)
+    y = torch.rand(n, dtype=torch.float64, device='cuda', generator=g)
+    kw = dict(range=[(0, 1), (0, 1)], bins=(1024, 1024))
+    device.deposit([x, y], None, shape=2, **kw)
+    assert _lib.last_probe()['mode'] == 'rows'                       # i.i.d. over a grid >> tile
+    o = torch.argsort(x)
+    device.deposit([x[o], y[o]], None, shape=2, **kw)
+    assert _lib.last_probe()['mode'] == 'rows'                       # x-ordered: a band of whole rows is no win
+    cell = (x * 1024).floor() * 1024 + (y * 1024).floor()
+    o = torch.argsort(cell)
+    xs, ys = x[o].contiguous(), y[o].contiguous()
+    device.deposit([xs, ys], None, shape=2, **kw)
+    assert _lib.last_probe()['mode'] == 'runs'                       # cell-ordered, even shape
+    device.deposit([xs, ys], None, shape=1, **kw)
+    assert _lib.last_probe()['mode'] == 'runs_wide'                  # cell-ordered, odd shape
+    xb = 0.45 + 0.1 * x
+    yb = 0.45 + 0.1 * y
+    device.deposit([xb, yb], None, shape=2, **kw)
+    p = _lib.last_probe()
+    assert p['mode'] == 'tiled' and p['ext'][0] * p['ext'][1] <= 25600     # a bunch that fits the tile
+    device.deposit([x], None, range=(0, 1), bins=1000, shape=1)
+    p = _lib.last_probe()
+    assert p['mode'] == 'tiled' and p['ext'][0] == 1002              # small 1-D histogram: whole grid in the tile
