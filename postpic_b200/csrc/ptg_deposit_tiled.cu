@@ -432,6 +432,97 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
 }
 
 // ---------------------------------------------------------------------------------
+// whole grid in shared memory (1-D spectra, small 2-D / 3-D histograms)
+// ---------------------------------------------------------------------------------
+// When the padded grid itself fits the tile there is no window to manage: a lean kernel keeps R
+// replicas of the grid in shared memory (warp w adds to replica w % R, dividing same-address
+// contention), streams the particles with kSU independent loads in flight per thread, and merges the
+// replicas into the global grid at the end.  This is the path of postpic's 1-D energy spectra.
+constexpr int kST = 1024;     // threads per CTA, one CTA per SM
+constexpr int kSU = 4;        // particles in flight per thread
+
+template <int ND, int S, bool W>
+__global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P, const TileConfig *gate) {
+    if (gate != nullptr && gate->mode != kModeTiled) return;
+    extern __shared__ double tile[];
+    constexpr int NW = StencilWidth<S>::value;
+    constexpr int SS = S == 0 ? 1 : S;
+    constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
+    const int cells = P.dims[0] * P.dims[1] * P.dims[2];
+    int replicas = kTileCells / cells;
+    if (replicas > kST / 32) replicas = kST / 32;
+    if (replicas < 1) replicas = 1;
+    for (int c = threadIdx.x; c < cells * replicas; c += kST) tile[c] = 0.0;
+    __syncthreads();
+    double *mine = tile + ((threadIdx.x >> 5) % replicas) * cells;
+    const int p1 = ND >= 2 ? P.dims[1] : 1, p2 = ND >= 3 ? P.dims[2] : 1;
+
+    auto one = [&](double x, double y, double z, double w) {
+        int b[3] = {0, 0, 0};
+        double wx[NW], wy[NW], wz[NW];
+        bool ok;
+        if constexpr (S == 0) {
+            ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], b[0]);
+            if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
+            if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
+            wx[0] = wy[0] = wz[0] = 1.0;
+        } else {
+            double (&rx)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wx);
+            double (&ry)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wy);
+            double (&rz)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wz);
+            ok = shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b[0], rx);
+            if (ND >= 2) ok = shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], b[1], ry) && ok;
+            if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b[2], rz) && ok;
+        }
+        if (!ok) return;
+        double *t = mine + (b[0] * p1 + b[1]) * p2 + b[2];
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                for (int d = 0; d < NDD; ++d) {
+                    double v;
+                    if (S == 0) v = W ? w : 1.0;
+                    else if (ND == 1) v = W ? __dmul_rn(wx[a], w) : wx[a];
+                    else {
+                        v = __dmul_rn(wx[a], wy[c]);
+                        if (ND == 3) v = __dmul_rn(v, wz[d]);
+                        if (W) v = __dmul_rn(v, w);
+                    }
+                    atomicAdd(t + (a * p1 + c) * p2 + d, v);
+                }
+    };
+
+    const int64_t nthreads = (int64_t)gridDim.x * kST;
+    int64_t i = (int64_t)blockIdx.x * kST + threadIdx.x;
+    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
+    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2], sw = P.stride[3];
+    for (; i + (kSU - 1) * nthreads < P.n; i += kSU * nthreads) {
+        double x[kSU], y[kSU], z[kSU], w[kSU];
+#pragma unroll
+        for (int u = 0; u < kSU; ++u) {
+            const int64_t k = i + u * nthreads;
+            x[u] = ld_stream(px + k * sx);
+            y[u] = ND >= 2 ? ld_stream(py + k * sy) : 0.0;
+            z[u] = ND >= 3 ? ld_stream(pz + k * sz) : 0.0;
+            w[u] = W ? ld_stream(pw + k * sw) : 1.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kSU; ++u) one(x[u], y[u], z[u], w[u]);
+    }
+    for (; i < P.n; i += nthreads)
+        one(ld_stream(px + i * sx), ND >= 2 ? ld_stream(py + i * sy) : 0.0, ND >= 3 ? ld_stream(pz + i * sz) : 0.0,
+            W ? ld_stream(pw + i * sw) : 1.0);
+    __syncthreads();
+    for (int c = threadIdx.x; c < cells; c += kST) {
+        double v = tile[c];
+        for (int r = 1; r < replicas; ++r) v = __dadd_rn(v, tile[r * cells + c]);
+        if (v != 0.0) red_add(P.grid + c, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
 template <int ND, int S, bool W>
@@ -444,6 +535,15 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_probe<ND, S><<<kProbeBlocks, kTT, 0, st>>>(P, cfg, force, runs_wide_available(ND, S) ? 1 : 0);
+    if ((int64_t)P.dims[0] * P.dims[1] * P.dims[2] <= kTileCells) {
+        // the whole padded grid fits the tile: lean kernel without window management
+        auto small = k_deposit_small<ND, S, W>;
+        e = cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int64_t want = (P.n + (int64_t)kST * kSU - 1) / ((int64_t)kST * kSU);
+        small<<<(int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count), kST, smem, st>>>(P, cfg);
+        return cudaGetLastError();
+    }
     kern<<<sm_count, TT, smem, st>>>(P, cfg);
     return cudaGetLastError();
 }
