@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--unweighted", action="store_true", help="weights=None (the reference's separate branch)")
+    ap.add_argument("--shape", type=int, default=None, help="override the workload's particle shape")
     ap.add_argument("--cpu-sample", type=float, default=2e7)
     ap.add_argument("--e2e-steps", type=int, default=None)
     return ap.parse_args()
@@ -297,12 +299,18 @@ def run_b200_arm(args):
 
     name = args.workload
     nd, shape, n_default, bins, ranges, desc = WORKLOADS[name]
+    if args.shape is not None:
+        shape = args.shape
+        desc += " [shape overridden: %d]" % shape
     n = int(args.n or n_default)
     method = None if args.method == "auto" else args.method
     coords, w = make_cloud_device(name, n, 2 + rank, args.order, dev)
+    if args.unweighted:
+        w = None
+        desc += " [unweighted]"
     plan = ptgdev.Plan(list(ranges), list(bins), shape)
     grid = torch.empty(plan.dims, dtype=torch.float64, device=dev)
-    bpp = BYTES_PER_PARTICLE[nd]
+    bpp = BYTES_PER_PARTICLE[nd] - (8 if args.unweighted else 0)
 
     def step():
         ptgdev.deposit_into(grid, plan, coords, w, method=method, zero=True)
@@ -372,7 +380,7 @@ def run_b200_arm(args):
             probe = None
 
     # parity spot-check of what was just timed (cheap: mass conservation incl. ghost cells)
-    tw = w.sum()
+    tw = w.sum() if w is not None else torch.tensor(float(n), dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tw, op=dist.ReduceOp.SUM)
     total_w = float(tw)
@@ -385,9 +393,9 @@ def run_b200_arm(args):
     e2e = None
     if not args.no_e2e:
         hc = [c.cpu().pin_memory() for c in coords]
-        hw = w.cpu().pin_memory()
+        hw = w.cpu().pin_memory() if w is not None else None
         np_c = [c.numpy() for c in hc]
-        np_w = hw.numpy()
+        np_w = hw.numpy() if hw is not None else None
         ptg_mod.method = method
         ptg_mod.device_index = local_rank
         ksteps = args.e2e_steps or max(3, min(args.steps, 5))
@@ -397,7 +405,7 @@ def run_b200_arm(args):
                 h, edges = histogramdd(tuple(np_c), weights=np_w, range=ranges, bins=list(bins), shape=shape)
                 return h
             dc = [c.to(dev, non_blocking=True) for c in hc]
-            dw = hw.to(dev, non_blocking=True)
+            dw = hw.to(dev, non_blocking=True) if hw is not None else None
             g, _ = parallel.deposit_sharded(dc, dw, range=ranges, bins=list(bins), shape=shape, method=method)
             return g.cpu()
         e2e_step()
@@ -415,7 +423,7 @@ def run_b200_arm(args):
         if world == 1:
             # the same call on ordinary (pageable) numpy arrays, as a postpic user would pass them
             pg_c = [np.array(c) for c in np_c]
-            pg_w = np.array(np_w)
+            pg_w = np.array(np_w) if np_w is not None else None
             histogramdd(tuple(pg_c), weights=pg_w, range=ranges, bins=list(bins), shape=shape)
             t0 = time.perf_counter()
             for _ in range(3):
@@ -436,6 +444,8 @@ def run_b200_arm(args):
         torch.cuda.empty_cache()
         for order in ("sorted", "cellsorted"):
             vc, vw = make_cloud_device(name, n, 2 + rank, order, dev)
+            if args.unweighted:
+                vw = None
             for _ in range(3):
                 ptgdev.deposit_into(grid, plan, vc, vw, method=method, zero=True)
             torch.cuda.synchronize()

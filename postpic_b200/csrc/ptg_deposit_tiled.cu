@@ -448,13 +448,21 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
     constexpr int NW = StencilWidth<S>::value;
     constexpr int SS = S == 0 ? 1 : S;
     constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
+    // Plain counting (shape 0, no weights -- numpy.histogram's job): every contribution is exactly 1,
+    // so the tile holds 32-bit counters and uses the one NATIVE shared-memory atomic of sm_100a
+    // (ATOMS.ADD.U32, 3.7x the rate of the fp64 CAS loop); the counts are exact and are converted to
+    // double at the merge.  A CTA sees fewer than 2^32 particles for any n < 148 * 2^32.
+    constexpr bool COUNT = (S == 0 && !W);
     const int cells = P.dims[0] * P.dims[1] * P.dims[2];
     int replicas = kTileCells / cells;
     if (replicas > kST / 32) replicas = kST / 32;
     if (replicas < 1) replicas = 1;
-    for (int c = threadIdx.x; c < cells * replicas; c += kST) tile[c] = 0.0;
+    unsigned *ctile = reinterpret_cast<unsigned *>(tile);
+    if (COUNT) { for (int c = threadIdx.x; c < cells * replicas; c += kST) ctile[c] = 0u; }
+    else       { for (int c = threadIdx.x; c < cells * replicas; c += kST) tile[c] = 0.0; }
     __syncthreads();
     double *mine = tile + ((threadIdx.x >> 5) % replicas) * cells;
+    unsigned *cmine = ctile + ((threadIdx.x >> 5) % replicas) * cells;
     const int p1 = ND >= 2 ? P.dims[1] : 1, p2 = ND >= 3 ? P.dims[2] : 1;
 
     auto one = [&](double x, double y, double z, double w) {
@@ -475,6 +483,10 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
             if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b[2], rz) && ok;
         }
         if (!ok) return;
+        if constexpr (COUNT) {
+            atomicAdd(cmine + (b[0] * p1 + b[1]) * p2 + b[2], 1u);
+            return;
+        }
         double *t = mine + (b[0] * p1 + b[1]) * p2 + b[2];
 #pragma unroll
         for (int a = 0; a < NA; ++a)
@@ -516,8 +528,15 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
             W ? ld_stream(pw + i * sw) : 1.0);
     __syncthreads();
     for (int c = threadIdx.x; c < cells; c += kST) {
-        double v = tile[c];
-        for (int r = 1; r < replicas; ++r) v = __dadd_rn(v, tile[r * cells + c]);
+        double v;
+        if (COUNT) {
+            unsigned long long k = ctile[c];
+            for (int r = 1; r < replicas; ++r) k += ctile[r * cells + c];
+            v = (double)k;
+        } else {
+            v = tile[c];
+            for (int r = 1; r < replicas; ++r) v = __dadd_rn(v, tile[r * cells + c]);
+        }
         if (v != 0.0) red_add(P.grid + c, v);
     }
 }
