@@ -145,7 +145,10 @@ void fill_params(ptg::DepositParams &P, int ndim, int shape, int64_t n, const do
     P.stag_copy = 0;
 }
 
-constexpr unsigned kCfgRing = 256;
+// Probe verdicts live in a ring: an AUTO/TILED call takes the next entry and its kernels read it in
+// stream order.  4096 entries = the number of such calls that may be in flight per device at once
+// (the host pipeline below never has more than 8).
+constexpr unsigned kCfgRing = 4096;
 
 std::mutex g_ring_mu;     // never held together with g_mu by the same call path in reverse order
 
@@ -479,9 +482,16 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
     int slot = 0;
     const int64_t chunk = direct ? kChunk : kStageChunk;
     bool slot_used[kSlots] = {};
-    for (int64_t off = 0; off < n; off += chunk, slot = (slot + 1) % kSlots) {
+    // bound the work queued ahead of the GPU: chunk c is only enqueued once chunk c - 8 has finished
+    constexpr int kInFlight = 8;
+    cudaEvent_t fin[kInFlight];
+    for (int k = 0; k < kInFlight; ++k) PTG_CUDA(cudaEventCreateWithFlags(&fin[k], cudaEventDisableTiming));
+    struct FinGuard { cudaEvent_t *e; ~FinGuard() { for (int k = 0; k < kInFlight; ++k) cudaEventDestroy(e[k]); } } fin_guard{fin};
+    int64_t cidx = 0;
+    for (int64_t off = 0; off < n; off += chunk, slot = (slot + 1) % kSlots, ++cidx) {
         const int64_t m = n - off < chunk ? n - off : chunk;
         cudaStream_t st = ordered ? d->stream[0] : d->stream[slot];
+        if (cidx >= kInFlight) PTG_CUDA(cudaEventSynchronize(fin[cidx % kInFlight]));
         double *dptr[4] = {nullptr, nullptr, nullptr, nullptr};
         if (direct) {
             for (int k = 0; k < 4; ++k) {
@@ -510,6 +520,7 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
         rc = deposit_device(d, ndim, shape, m, dptr[0], dptr[1], dptr[2], dptr[3], nullptr, lo, inv, bins,
                             d->grid, dflags, st);
         if (rc) { cudaEventDestroy(zeroed); return rc; }
+        PTG_CUDA(cudaEventRecord(fin[cidx % kInFlight], st));
     }
     // join the ring on stream 0, then bring the padded grid home
     for (int k = 1; k < kSlots; ++k) {
