@@ -352,6 +352,23 @@ def run_b200_arm(args):
         b.synchronize()
         durs.append(a.elapsed_time(b))
     k_ms = sum(durs) / len(durs)
+    k_best, k_median = min(durs), statistics.median(durs)
+
+    # the exchange step alone (N > 1): one all-reduce of the padded grid, timed like the kernel
+    allreduce_ms = None
+    if world > 1:
+        ar = []
+        for _ in range(args.steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            a.record()
+            dist.all_reduce(grid, op=dist.ReduceOp.SUM)
+            b.record()
+            b.synchronize()
+            ar.append(a.elapsed_time(b))
+        t = torch.tensor([statistics.median(ar)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allreduce_ms = float(t.item())
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -368,7 +385,9 @@ def run_b200_arm(args):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel_ms": k_ms, "bytes_per_particle": bpp,
+                "traffic": traffic, "kernel_ms": k_ms, "kernel_ms_best": k_best, "kernel_ms_median": k_median,
+                "allreduce_ms": allreduce_ms, "allreduce_bytes": plan.cells * 8 if world > 1 else None,
+                "bytes_per_particle": bpp,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 

@@ -112,6 +112,22 @@ int ptg_minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, voi
 int ptg_scale_f64(double *grid, int64_t count, double factor, void *stream);
 int ptg_zero_f64(double *grid, int64_t count, void *stream);
 
+/* ---- per-particle weight expressions in one pass (the step before the path) --------------- */
+/* out[i] = weight[i] * f(px[i], py[i], pz[i]) (weight NULL = 1) for the kinetic scalars of postpic's
+ * default scalar context (scalarproperties.py:183-205), which MultiSpecies._createHistgram
+ * evaluates as `weight * (expr)` through numexpr (particles.py:1097).  Device pointers; strides[4]
+ * (px, py, pz, weight) in doubles or NULL.  mass in kg; c and elementary_charge are passed in so
+ * that the caller's constants (scipy.constants in the reference) are used.                       */
+#define PTG_W_GAMMA_M1 1
+#define PTG_W_GAMMA    2
+#define PTG_W_EKIN     3   /* J   */
+#define PTG_W_EKIN_MEV 4
+#define PTG_W_EKIN_KEV 5
+#define PTG_W_P        6   /* |p| */
+int ptg_weights_f64(int kind, int64_t n, const double *px, const double *py, const double *pz,
+                    const double *weight, const int64_t *strides, double mass, double c, double elementary_charge,
+                    double *out, void *stream);
+
 /* ---- host-buffer drop-in: H2D + deposit + D2H in one call --------------------------- */
 /*
  * Same meaning as ptg_deposit_f64 but x,y,z,w and grid are HOST pointers.  Particles

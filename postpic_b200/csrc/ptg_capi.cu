@@ -434,6 +434,19 @@ int ptg_scale_f64(double *grid, int64_t count, double factor, void *stream) {
     return PTG_OK;
 }
 
+int ptg_weights_f64(int kind, int64_t n, const double *px, const double *py, const double *pz,
+                    const double *weight, const int64_t *strides, double mass, double c, double elementary_charge,
+                    double *out, void *stream) {
+    if (kind < PTG_W_GAMMA_M1 || kind > PTG_W_P) return fail(PTG_EINVAL, "unknown weight expression kind %d", kind);
+    if (n < 0 || (n > 0 && (!px || !py || !pz || !out))) return fail(PTG_EINVAL, "ptg_weights_f64: bad arguments");
+    DeviceState *d;
+    int rc = current_device_state(&d);
+    if (rc) return rc;
+    PTG_CUDA(ptg::weights_f64(kind, n, px, py, pz, weight, strides, mass, c, elementary_charge, out, d->sm_count,
+                              (cudaStream_t)stream));
+    return PTG_OK;
+}
+
 int ptg_zero_f64(double *grid, int64_t count, void *stream) {
     if (!grid || count < 0) return fail(PTG_EINVAL, "ptg_zero_f64: bad arguments");
     DeviceState *d;

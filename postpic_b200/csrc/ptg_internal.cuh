@@ -51,6 +51,9 @@ cudaError_t deposit_sorted(int ndim, int shape, const DepositParams &P, void *ws
 cudaError_t minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, int sm_count,
                        cudaStream_t st);
 cudaError_t scale_f64(double *grid, int64_t count, double factor, int sm_count, cudaStream_t st);
+cudaError_t weights_f64(int kind, int64_t n, const double *px, const double *py, const double *pz,
+                        const double *weight, const int64_t *strides, double mass, double c, double qe, double *out,
+                        int sm_count, cudaStream_t st);
 cudaError_t selftest_div6(int64_t n, const double *in, double *out, cudaStream_t st);
 
 }  // namespace ptg

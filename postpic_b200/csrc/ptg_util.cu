@@ -89,6 +89,58 @@ cudaError_t scale_f64(double *grid, int64_t count, double factor, int sm_count, 
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------
+// per-particle weight expressions in one pass
+// ---------------------------------------------------------------------------------
+// out[i] = weight[i] * f(px[i], py[i], pz[i]) for the kinetic scalars of postpic's default scalar
+// context (/root/reference/postpic/particles/scalarproperties.py:183-205), evaluated in the order the
+// nested expressions prescribe:
+//   _np2     = (px**2 + py**2 + pz**2) / (mass * c)**2
+//   gamma_m1 = _np2 / (sqrt(1 + _np2) + 1)
+//   Ekin     = gamma_m1 * mass * c**2          Ekin_MeV = Ekin / elementary_charge / 1e6
+// The reference gets there through ~10 numexpr passes and as many N-sized temporaries; here it is one
+// read of px, py, pz (+ weight) and one write.
+__global__ void __launch_bounds__(256) k_weights(int kind, int64_t n, const double *px, const double *py,
+                                                 const double *pz, const double *weight, int64_t s0, int64_t s1,
+                                                 int64_t s2, int64_t s3, double mass, double c, double qe,
+                                                 double *out) {
+    const double mc = __dmul_rn(mass, c);
+    const double mc2 = __dmul_rn(mc, mc);                  // (mass * c)**2
+    const double c2 = __dmul_rn(c, c);                      // c**2
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const double x = ld_stream(px + i * s0), y = ld_stream(py + i * s1), z = ld_stream(pz + i * s2);
+        const double p2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+        double v;
+        if (kind == 6) {
+            v = sqrt(p2);                                                   // p
+        } else {
+            const double np2 = p2 / mc2;
+            const double gm1 = np2 / __dadd_rn(sqrt(__dadd_rn(1.0, np2)), 1.0);
+            switch (kind) {
+                case 1: v = gm1; break;                                                     // gamma_m1
+                case 2: v = __dadd_rn(gm1, 1.0); break;                                     // gamma
+                case 3: v = __dmul_rn(__dmul_rn(gm1, mass), c2); break;                     // Ekin [J]
+                case 4: v = __dmul_rn(__dmul_rn(gm1, mass), c2) / qe / 1e6; break;          // Ekin_MeV
+                default: v = __dmul_rn(__dmul_rn(gm1, mass), c2) / qe / 1e3; break;         // Ekin_keV
+            }
+        }
+        out[i] = weight ? __dmul_rn(ld_stream(weight + i * s3), v) : v;
+    }
+}
+
+cudaError_t weights_f64(int kind, int64_t n, const double *px, const double *py, const double *pz,
+                        const double *weight, const int64_t *strides, double mass, double c, double qe, double *out,
+                        int sm_count, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    int64_t want = (n + 256 * 4 - 1) / (256 * 4);
+    int64_t cap = (int64_t)sm_count * 8;
+    k_weights<<<(int)(want < cap ? want : cap), 256, 0, st>>>(kind, n, px, py, pz, weight, strides ? strides[0] : 1,
+                                                             strides ? strides[1] : 1, strides ? strides[2] : 1,
+                                                             strides ? strides[3] : 1, mass, c, qe, out);
+    return cudaGetLastError();
+}
+
 __global__ void k_div6(int64_t n, const double *in, double *out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = div6(in[i]);

@@ -132,3 +132,26 @@ def scale_(grid, factor):
         _lib.check(_lib.load().ptg_scale_f64(grid.data_ptr(), grid.numel(), float(factor),
                                              torch.cuda.current_stream().cuda_stream))
     return grid
+
+
+WEIGHT_KINDS = {'gamma_m1': 1, 'gamma': 2, 'Ekin': 3, 'Ekin_MeV': 4, 'Ekin_keV': 5, 'p': 6}
+
+
+def kinetic_weights(kind, px, py, pz, weight=None, mass=None, c=299792458.0, elementary_charge=1.602176634e-19):
+    """weight * <kind>(px, py, pz) in one pass on the device (kind: gamma_m1, gamma, Ekin, Ekin_MeV,
+    Ekin_keV, p) -- the `weight * (expr)` of particles.py:1097 without numexpr's temporaries."""
+    torch = _torch()
+    for t, nm in ((px, 'px'), (py, 'py'), (pz, 'pz')):
+        _check_tensor(t, nm)
+    if weight is not None:
+        _check_tensor(weight, 'weight')
+    n = px.numel()
+    out = torch.empty(n, dtype=torch.float64, device=px.device)
+    strides = (ctypes.c_int64 * 4)(*[t.stride(0) if n > 1 else 1 for t in (px, py, pz)],
+                                   weight.stride(0) if (weight is not None and n > 1) else 1)
+    with torch.cuda.device(px.device):
+        _lib.check(_lib.load().ptg_weights_f64(
+            WEIGHT_KINDS[kind], n, px.data_ptr(), py.data_ptr(), pz.data_ptr(),
+            weight.data_ptr() if weight is not None else None, strides, float(mass if mass is not None else 1.0),
+            float(c), float(elementary_charge), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return out

@@ -263,6 +263,32 @@ class MultiSpecies(object):
             return _device._torch().cat(parts)
         return np.hstack(parts)
 
+    def _weights(self, weights):
+        """`weight * (weights)` per particle (particles.py:1097).  Device-resident species whose extra
+        weight is one of the kinetic scalars (gamma, gamma_m1, Ekin, Ekin_MeV, Ekin_keV, p) are evaluated
+        by one fused CUDA pass over px, py, pz, weight (ptg_weights_f64) instead of the chain of
+        expression temporaries; everything else goes through the generic evaluator."""
+        key = getattr(weights, 'symbol', weights)
+        fusable = (isinstance(key, str) and key in _device.WEIGHT_KINDS and self._sources and
+                   all(s.device is not None and all(_device.is_cuda_tensor(s._arrays.get(k)) for k in ('px', 'py', 'pz'))
+                       and np.ndim(s._arrays.get('mass', None)) == 0 and s._arrays.get('mass', None) is not None
+                       for s in self._sources))
+        if not fusable:
+            return self('weight * ({})'.format(weights))
+        parts = []
+        for s in self._sources:
+            wt = s._arrays.get('weight', 1.0)
+            wt_t = wt if _device.is_cuda_tensor(wt) else None
+            out = _device.kinetic_weights(key, s._arrays['px'], s._arrays['py'], s._arrays['pz'], wt_t,
+                                          mass=float(s._arrays['mass']),
+                                          c=_sc.c if _sc is not None else _CONSTANTS['c'],
+                                          elementary_charge=(_sc.elementary_charge if _sc is not None
+                                                             else _CONSTANTS['elementary_charge']))
+            if wt_t is None and float(wt) != 1.0:
+                out *= float(wt)
+            parts.append(out)
+        return parts[0] if len(parts) == 1 else _device._torch().cat(parts)
+
     # -- the dispatch ------------------------------------------------------------------
     def _createHistgram(self, *sps, **kwargs):
         """(h, edges) of a 1-, 2- or 3-D deposit of this particle collection, divided by
@@ -309,7 +335,7 @@ class MultiSpecies(object):
             edges = [edges_of(r, bins[i]) for i, r in zip(range(h.ndim), ranges)]
             return h, edges
 
-        w = self('weight * ({})'.format(weights))
+        w = self._weights(weights)
         h, edges = histogramdd(data, weights=w, range=ranges, bins=bins, shape=shape)
         dV = np.prod([edge[1] - edge[0] for edge in edges])
         h /= dV

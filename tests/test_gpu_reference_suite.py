@@ -196,6 +196,32 @@ class TestCreateField:
         fd = pd.createField('x', 'y', **kw)
         assert np.allclose(fd.matrix, f.matrix, rtol=1e-10, atol=1e-300)
 
+    @pytest.mark.parametrize("kind", ['gamma_m1', 'gamma', 'Ekin', 'Ekin_MeV', 'Ekin_keV', 'p'])
+    def test_fused_kinetic_weights_match_the_expression_chain(self, kind):
+        """ptg_weights_f64 (one pass) against the scalar definitions of scalarproperties.py:183-205
+        evaluated with numpy; tolerance 1e-14 relative (same operations, same order)."""
+        import scipy.constants as sc
+        import torch
+        from postpic_b200 import device
+        rng = np.random.default_rng(5)
+        n = 200001
+        me = 9.109383e-31
+        px, py, pz = (rng.normal(0, 1, n) * me * sc.c * 3 for _ in range(3))
+        wt = rng.uniform(0.5, 2, n)
+        np2 = (px ** 2 + py ** 2 + pz ** 2) / (me * sc.c) ** 2
+        gm1 = np2 / (np.sqrt(1 + np2) + 1)
+        expect = {'gamma_m1': gm1, 'gamma': gm1 + 1, 'Ekin': gm1 * me * sc.c ** 2,
+                  'Ekin_MeV': gm1 * me * sc.c ** 2 / sc.elementary_charge / 1e6,
+                  'Ekin_keV': gm1 * me * sc.c ** 2 / sc.elementary_charge / 1e3,
+                  'p': np.sqrt(px ** 2 + py ** 2 + pz ** 2)}[kind]
+        t = [torch.from_numpy(a).cuda() for a in (px, py, pz, wt)]
+        got = device.kinetic_weights(kind, t[0], t[1], t[2], t[3], mass=me, c=sc.c,
+                                     elementary_charge=sc.elementary_charge).cpu().numpy()
+        assert np.allclose(got, wt * expect, rtol=1e-14, atol=0)
+        got = device.kinetic_weights(kind, t[0][::2], t[1][::2], t[2][::2], None, mass=me, c=sc.c,
+                                     elementary_charge=sc.elementary_charge).cpu().numpy()
+        assert np.allclose(got, expect[::2], rtol=1e-14, atol=0)
+
     def test_empty_and_aliases(self):
         from postpic_b200 import MultiSpecies, ArraySource
         empty = MultiSpecies(ArraySource('none', dict(x=np.empty(0), y=np.empty(0), weight=np.empty(0))))
