@@ -50,7 +50,6 @@ struct DeviceState {
     double *slot[kSlots] = {};                    // each 4 * kChunk doubles
     double *grid = nullptr;
     int64_t grid_cells = 0;
-    double *scratch2 = nullptr;                   // 2 doubles for min/max
     bool staged = false;
     // pinned host ring for pageable / strided sources (filled by worker threads, then DMA'd)
     double *pinned[kSlots] = {};
@@ -245,7 +244,6 @@ int ensure_staging(DeviceState *d, int64_t cells) {
             PTG_CUDA(cudaStreamCreateWithFlags(&d->stream[k], cudaStreamNonBlocking));
             PTG_CUDA(cudaMalloc(&d->slot[k], (size_t)4 * kChunk * sizeof(double)));
         }
-        PTG_CUDA(cudaMalloc(&d->scratch2, 2 * sizeof(double)));
         d->staged = true;
     }
     if (cells > d->grid_cells) {
@@ -610,10 +608,9 @@ int ptg_release(void) {
             d.stream[k] = nullptr;
         }
         if (d.grid) cudaFree(d.grid);
-        if (d.scratch2) cudaFree(d.scratch2);
         if (d.cfg_ring) cudaFree(d.cfg_ring);
         d.cfg_ring = nullptr;
-        d.grid = nullptr; d.scratch2 = nullptr; d.grid_cells = 0; d.staged = false; d.pinned_ready = false;
+        d.grid = nullptr; d.grid_cells = 0; d.staged = false; d.pinned_ready = false;
     }
     cudaSetDevice(prev);
     return PTG_OK;
