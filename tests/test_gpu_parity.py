@@ -450,3 +450,38 @@ def test_auto_probe_verdicts():
     device.deposit([x], None, range=(0, 1), bins=1000, shape=1)
     p = _lib.last_probe()
     assert p['mode'] == 'tiled' and p['ext'][0] == 1002              # small 1-D histogram: whole grid in the tile
+
+
+@pytest.mark.parametrize("method", METHODS)
+@pytest.mark.parametrize("nd,shape", [(nd, s) for nd in (1, 2, 3) for s in (0, 1, 2, 3)])
+def test_no_write_outside_the_padded_grid(nd, shape, method):
+    """Guard zones on both sides of the grid must stay untouched (compute-sanitizer is not available on
+    this pool, so out-of-bounds reductions are hunted with canaries): particles overshoot the range on
+    every side, sit exactly on the edges, and include NaN / inf coordinates."""
+    import torch
+    from postpic_b200 import device
+    _skip_unavailable(method, nd, shape)
+    bins = [(61,), (23, 17), (9, 8, 7)][nd - 1]
+    plan = device.Plan([(0.0, 1.0)] * nd, list(bins), shape)
+    guard = 8192
+    buf = torch.zeros(plan.cells + 2 * guard, dtype=torch.float64, device='cuda')
+    grid = buf[guard:guard + plan.cells].view(plan.dims)
+    g = torch.Generator(device='cuda').manual_seed(17 * nd + shape)
+    n = 300000
+    coords = [torch.rand(n, dtype=torch.float64, device='cuda', generator=g) * 1.6 - 0.3 for _ in range(nd)]
+    special = torch.tensor([0.0, 1.0, -0.0, float('nan'), float('inf'), float('-inf'), 1e300, -1e300, 3e9,
+                            1.0 - 1e-16, 1.0 + 1e-12, -1e-12], dtype=torch.float64, device='cuda')
+    for c in coords:
+        c[:special.numel()] = special
+        c[special.numel():2 * special.numel()] = special.flip(0)
+    # cell-ordered copy as well, so that the run-length kernels take their aggregated paths
+    key = torch.zeros(n, dtype=torch.float64, device='cuda')
+    for c in coords:
+        key = key * 64 + torch.nan_to_num(c, nan=0.0, posinf=2.0, neginf=-1.0).clamp(-1, 2).mul(20).floor()
+    order = torch.argsort(key)
+    w = torch.rand(n, dtype=torch.float64, device='cuda', generator=g)
+    for cs, ws in ((coords, w), ([c[order].contiguous() for c in coords], w[order].contiguous()), (coords, None)):
+        device.deposit_into(grid, plan, cs, ws, method=method, zero=True)
+        torch.cuda.synchronize()
+        assert not buf[:guard].any() and not buf[guard + plan.cells:].any()
+        assert torch.isfinite(grid).all()
