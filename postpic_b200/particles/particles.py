@@ -335,11 +335,47 @@ class MultiSpecies(object):
             edges = [edges_of(r, bins[i]) for i, r in zip(range(h.ndim), ranges)]
             return h, edges
 
+        if len(self._sources) > 1 and all(s.device is not None for s in self._sources):
+            return self._createHistgram_per_species(sps, ranges, weights, bins, shape)
         w = self._weights(weights)
         h, edges = histogramdd(data, weights=w, range=ranges, bins=bins, shape=shape)
         dV = np.prod([edge[1] - edge[0] for edge in edges])
         h /= dV
         return h, edges
+
+    def _createHistgram_per_species(self, sps, ranges, weights, bins, shape):
+        """Several device-resident species: deposition is linear in the particle set, so every
+        species is deposited into the SAME device grid, one after the other, instead of first
+        concatenating all per-particle arrays (the np.hstack of particles.py:662-674).  The
+        1/dV scaling also happens on the device; only the finished grid crosses PCIe."""
+        from .._setup import as_bins
+        from ._routines import _DEFAULT_BINS
+        torch = _device._torch()
+        nd = len(sps)
+        singles = [MultiSpecies(s) for s in self._sources]
+        per = [([m(sp) for sp in sps], m._weights(weights)) for m in singles if len(m) > 0]
+        per = [(d if all(_device.is_cuda_tensor(a) for a in d) else [torch.as_tensor(np.asarray(a), device=self._sources[0].device) for a in d], w) for d, w in per]
+        rng = []
+        for a in range(nd):
+            r = ranges[a]
+            lo, hi = (None, None) if r is None else (r[0], r[1])
+            if lo is None or hi is None:
+                mm = [_device.minmax(d[a].contiguous() if d[a].stride(0) < 1 else d[a]) for d, _ in per]
+                lo = min(m[0] for m in mm) if lo is None else lo
+                hi = max(m[1] for m in mm) if hi is None else hi
+            rng.append((lo, hi))
+        if bins is None:
+            bins = _DEFAULT_BINS[nd]
+        elif np.isscalar(bins):
+            bins = (bins,) * nd
+        plan = _device.Plan(rng, as_bins(bins[0] if nd == 1 else bins, nd), 2 if shape is None else shape)
+        grid = torch.zeros(plan.dims, dtype=torch.float64, device=self._sources[0].device)
+        for d, w in per:
+            _device.deposit_into(grid, plan, [t if t.dtype == torch.float64 else t.to(torch.float64) for t in d],
+                                 w if (w is None or w.dtype == torch.float64) else w.to(torch.float64), zero=False)
+        _device.scale_(grid, 1.0 / plan.cell_volume())
+        h = grid.cpu().numpy()[plan.interior]
+        return h, tuple(plan.edges)
 
     def createHistgram1d(self, spx, **kwargs):
         return self._createHistgram(spx, **kwargs)

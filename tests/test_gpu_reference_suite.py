@@ -222,6 +222,26 @@ class TestCreateField:
                                      elementary_charge=sc.elementary_charge).cpu().numpy()
         assert np.allclose(got, expect[::2], rtol=1e-14, atol=0)
 
+    def test_multi_species_on_device_deposits_without_concatenation(self):
+        from postpic_b200 import MultiSpecies, ArraySource
+        import torch
+        a, b = self._species(30000), self._species(20000)
+        b._arrays['x'] = b._arrays['x'] + 0.5
+        host = MultiSpecies(a, b)
+
+        def dev(src):
+            return ArraySource(src.species, {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v)
+                                             for k, v in src._arrays.items()}, extent=src.extent)
+        device_ms = MultiSpecies(dev(a), dev(b))
+        for kw in (dict(bins=[64, 48], rangex=(-3, 3), rangey=(-3, 3), shape=2),
+                   dict(bins=[64, 48], shape=3, weights='Ekin_MeV'),                 # ranges from the data
+                   dict(bins=[32, 32], simextent=True, shape=1, weights='gamma')):
+            fh = host.createField('x', 'y', **kw)
+            fd = device_ms.createField('x', 'y', **kw)
+            assert all(np.array_equal(p.grid_node, q.grid_node) for p, q in zip(fh.axes, fd.axes))
+            assert np.allclose(fd.matrix, fh.matrix, rtol=1e-10, atol=1e-12 * np.abs(fh.matrix).max())
+            assert fd.matrix.base is not None and fd.infostring == '50000 npart in 2 species'
+
     def test_empty_and_aliases(self):
         from postpic_b200 import MultiSpecies, ArraySource
         empty = MultiSpecies(ArraySource('none', dict(x=np.empty(0), y=np.empty(0), weight=np.empty(0))))
