@@ -303,6 +303,30 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------
+def launches_per_step(method, nd, shape, n, plan):
+    """Kernels of libptg_b200 launched per deposit call (checked against the ncu launch list in
+    profiles/r01/launches_cfg2_auto_final_summary.txt): AUTO = probe + tiled + runs (+ runs_wide where
+    it exists) + rows (+ the merge of the staggered staging grid); memsets are not kernels."""
+    nw = 1 if shape == 0 else shape + 1
+    wide = (nw + 1) ** nd <= 27
+    last = plan.dims[-1]
+    staged_bytes = 2 * (plan.cells // last * ((last + 2 + 3) // 4 * 4) + 4) * 8
+    stagger = shape in (1, 2) and staged_bytes <= (64 << 20) and n >= (1 << 20) and plan.cells * 8 <= (96 << 20)
+    passes = 1 if plan.cells * 8 <= (96 << 20) or n < (1 << 22) else -(-plan.cells * 8 // (72 << 20))
+    rows = passes * (2 if stagger else 1)
+    if method in ("rows",):
+        return rows
+    if method == "auto":
+        if n < (1 << 21):
+            return 2 if plan.cells <= 25600 else rows
+        return 1 + 1 + 1 + (1 if wide else 0) + rows
+    if method == "tiled":
+        return 2
+    if method == "sorted":
+        return 2 + 3 + 2 * nw ** nd            # keys, offsets, ~3 CUB kernels, two reduce launches per colour
+    return 1
+
+
 def run_b200_arm(args):
     import numpy as np
     import torch
@@ -522,7 +546,7 @@ def run_b200_arm(args):
                        "parallelism": "particles sharded over %d GPU(s), private grids, NCCL all-reduce" % world
                        if world > 1 else "1 GPU", "device": info["name"], "sm_count": info["sm_count"]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "variants": variants,
-            "gpu_launches": args.steps * world * {"auto": 4, "tiled": 2}.get(args.method, 1),
+            "gpu_launches": args.steps * world * launches_per_step(args.method, nd, shape, n, plan),
             "clocks": clocks.summary(),
             "parity": {"mass_conservation_rel_err": mass_err}, "auto_probe": probe,
         }
