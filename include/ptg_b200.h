@@ -88,8 +88,10 @@ int ptg_axis_setup(double lo_in, double hi_in, int bins, double *lo, double *hi,
 /*
  * x,y,z,w: device pointers (y,z ignored beyond ndim; w NULL = the reference's
  * `weights is None` branch).  grid: device pointer to the padded accumulator.
- * The call is asynchronous on `stream`.  workspace may be NULL when
- * ptg_workspace_bytes() returns 0 for the same arguments.
+ * The call is asynchronous on `stream`.  Scratch memory (method SORTED's sort buffers, the
+ * staggered staging grid of ROWS) is taken from `workspace` when ptg_workspace_bytes() bytes
+ * are supplied for SORTED, and otherwise from the device's stream-ordered memory pool
+ * (cudaMallocAsync on `stream`, no synchronisation); workspace may always be NULL.
  */
 int ptg_deposit_f64(int ndim, int shape, int64_t n,
                     const double *x, const double *y, const double *z, const double *w,

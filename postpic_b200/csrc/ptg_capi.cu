@@ -189,8 +189,9 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
             break;
         case PTG_METHOD_TILED:
         case PTG_METHOD_AUTO: {
-            // probe -> (tiled kernel | rows kernel): both are launched, the probe's verdict in device
-            // memory decides which one returns immediately; no host round trip.
+            // probe -> {tiled | runs | runs_wide | rows}: all candidates are launched back to back, the
+            // probe's verdict in device memory lets exactly one of them do the work and the others
+            // return at once; no host round trip, the call stays asynchronous.
             if (n <= 0) break;
             ptg::TileConfig *cfg;
             int rc = next_tile_config(d, &cfg);
