@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="weights = weight * Ekin_MeV(px,py,pz) evaluated inside the deposit kernel (48 B/particle in 2-D)")
     ap.add_argument("--unweighted", action="store_true", help="weights=None (the reference's separate branch)")
     ap.add_argument("--shape", type=int, default=None, help="override the workload's particle shape")
     ap.add_argument("--cpu-sample", type=float, default=2e7)
@@ -361,9 +362,19 @@ def run_b200_arm(args):
     plan = ptgdev.Plan(list(ranges), list(bins), shape)
     grid = torch.empty(plan.dims, dtype=torch.float64, device=dev)
     bpp = BYTES_PER_PARTICLE[nd] - (8 if args.unweighted else 0)
+    fused = None
+    if args.fused:
+        # thermal electron momenta, p ~ N(0, (0.1 me c)^2) per axis
+        me, c0 = 9.1093837015e-31, 299792458.0
+        g2 = torch.Generator(device=dev).manual_seed(77 + rank)
+        mom = [0.1 * me * c0 * torch.randn(n, dtype=torch.float64, device=dev, generator=g2) for _ in range(3)]
+        fused = dict(kind='Ekin_MeV', px=mom[0], py=mom[1], pz=mom[2], mass=me, c=c0)
+        w = torch.ones(n, dtype=torch.float64, device=dev)          # the macro-particle weight array
+        bpp += 24
+        desc += " [weight * Ekin_MeV fused into the deposit kernel]"
 
     def step():
-        ptgdev.deposit_into(grid, plan, coords, w, method=method, zero=True)
+        ptgdev.deposit_into(grid, plan, coords, w, method=method, zero=True, fused=fused)
         if world > 1:
             dist.all_reduce(grid, op=dist.ReduceOp.SUM)
 
@@ -397,7 +408,7 @@ def run_b200_arm(args):
         grid.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        ptgdev.deposit_into(grid, plan, coords, w, method=method, zero=False)
+        ptgdev.deposit_into(grid, plan, coords, w, method=method, zero=False, fused=fused)
         b.record()
         b.synchronize()
         durs.append(a.elapsed_time(b))
@@ -449,7 +460,11 @@ def run_b200_arm(args):
             probe = None
 
     # parity spot-check of what was just timed (cheap: mass conservation incl. ghost cells)
-    tw = w.sum() if w is not None else torch.tensor(float(n), dtype=torch.float64, device=dev)
+    if fused is not None:
+        tw = ptgdev.kinetic_weights('Ekin_MeV', fused['px'], fused['py'], fused['pz'], w, mass=fused['mass'],
+                                    c=fused['c']).sum()
+    else:
+        tw = w.sum() if w is not None else torch.tensor(float(n), dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tw, op=dist.ReduceOp.SUM)
     total_w = float(tw)

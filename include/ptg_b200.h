@@ -130,6 +130,19 @@ int ptg_weights_f64(int kind, int64_t n, const double *px, const double *py, con
                     const double *weight, const int64_t *strides, double mass, double c, double elementary_charge,
                     double *out, void *stream);
 
+/* The same expression evaluated INSIDE the deposit kernels (no weights array is written or re-read):
+ * ptg_deposit_f64 with the particle weight replaced by w[i] * f(px[i], py[i], pz[i]) (w NULL = 1).
+ * This is `createField(..., weights='Ekin_MeV')` of particles.py:1097-1100 in one pass over
+ * x, y(, z), px, py, pz, weight.  pstrides[3] in doubles or NULL; all pointers device pointers.      */
+int ptg_deposit_fused_f64(int ndim, int shape, int64_t n,
+                          const double *x, const double *y, const double *z, const double *w,
+                          const int64_t *strides,
+                          const double *lo, const double *inv, const int *bins,
+                          double *grid, unsigned flags,
+                          int kind, const double *px, const double *py, const double *pz,
+                          const int64_t *pstrides, double mass, double c, double elementary_charge,
+                          void *stream);
+
 /* ---- host-buffer drop-in: H2D + deposit + D2H in one call --------------------------- */
 /*
  * Same meaning as ptg_deposit_f64 but x,y,z,w and grid are HOST pointers.  Particles

@@ -52,6 +52,8 @@ SIGNATURES = {
     "ptg_axis_setup": (_c.c_int, [_c.c_double, _c.c_double, _c.c_int, _P, _P, _P]),
     "ptg_deposit_f64": (_c.c_int, [_c.c_int, _c.c_int, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                    _c.c_uint, _P, _c.c_size_t, _P]),
+    "ptg_deposit_fused_f64": (_c.c_int, [_c.c_int, _c.c_int, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _c.c_uint,
+                                         _c.c_int, _P, _P, _P, _P, _c.c_double, _c.c_double, _c.c_double, _P]),
     "ptg_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _I64, _P, _c.c_uint]),
     "ptg_padded_cells": (_I64, [_c.c_int, _c.c_int, _P]),
     "ptg_minmax_f64": (_c.c_int, [_I64, _P, _I64, _P, _P]),

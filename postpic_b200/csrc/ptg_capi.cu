@@ -142,7 +142,15 @@ void fill_params(ptg::DepositParams &P, int ndim, int shape, int64_t n, const do
     P.stag = nullptr;
     P.stag_pitch = 0;
     P.stag_copy = 0;
+    P.fuse_kind = 0;            // (memset above already cleared q / qstride / f_*)
 }
+
+struct FuseSpec {
+    int kind;
+    const double *q[3];
+    int64_t qstride[3];
+    double mass, c, qe;
+};
 
 // Probe verdicts live in a ring: an AUTO/TILED call takes the next entry and its kernels read it in
 // stream order.  4096 entries = the number of such calls that may be in flight per device at once
@@ -168,9 +176,17 @@ int next_tile_config(DeviceState *d, ptg::TileConfig **out) {
 int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double *x, const double *y,
                    const double *z, const double *w, const int64_t *strides, const double *lo,
                    const double *inv, const int *bins, double *grid, unsigned flags, cudaStream_t st,
-                   void *workspace = nullptr, size_t workspace_bytes = 0) {
+                   void *workspace = nullptr, size_t workspace_bytes = 0, const FuseSpec *fuse = nullptr) {
     ptg::DepositParams P;
     fill_params(P, ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid);
+    if (fuse) {
+        P.fuse_kind = fuse->kind;
+        for (int k = 0; k < 3; ++k) { P.q[k] = fuse->q[k]; P.qstride[k] = fuse->qstride[k]; }
+        P.f_mass = fuse->mass;
+        P.f_mc2 = (fuse->mass * fuse->c) * (fuse->mass * fuse->c);
+        P.f_c2 = fuse->c * fuse->c;
+        P.f_qe = fuse->qe;
+    }
     if (flags & PTG_ZERO_GRID)
         PTG_CUDA(cudaMemsetAsync(grid, 0, (size_t)ptg_padded_cells(ndim, shape, bins) * sizeof(double), st));
     unsigned method = flags & PTG_METHOD_MASK;
@@ -413,6 +429,26 @@ int ptg_deposit_f64(int ndim, int shape, int64_t n, const double *x, const doubl
     if ((rc = current_device_state(&d))) return rc;
     return deposit_device(d, ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid, flags,
                           (cudaStream_t)stream, workspace, workspace_bytes);
+}
+
+int ptg_deposit_fused_f64(int ndim, int shape, int64_t n, const double *x, const double *y, const double *z,
+                          const double *w, const int64_t *strides, const double *lo, const double *inv,
+                          const int *bins, double *grid, unsigned flags, int kind, const double *px,
+                          const double *py, const double *pz, const int64_t *pstrides, double mass, double c,
+                          double elementary_charge, void *stream) {
+    int rc = validate(ndim, shape, n, x, y, z, lo, inv, bins, grid);
+    if (rc) return rc;
+    if (kind < PTG_W_GAMMA_M1 || kind > PTG_W_P) return fail(PTG_EINVAL, "unknown weight expression kind %d", kind);
+    if (n > 0 && (!px || !py || !pz)) return fail(PTG_EINVAL, "momentum pointer is NULL");
+    DeviceState *d;
+    if ((rc = current_device_state(&d))) return rc;
+    FuseSpec f;
+    f.kind = kind;
+    f.q[0] = px; f.q[1] = py; f.q[2] = pz;
+    for (int k = 0; k < 3; ++k) f.qstride[k] = pstrides ? pstrides[k] : 1;
+    f.mass = mass; f.c = c; f.qe = elementary_charge;
+    return deposit_device(d, ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid, flags, (cudaStream_t)stream,
+                          nullptr, 0, &f);
 }
 
 int ptg_minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, void *stream) {

@@ -80,13 +80,13 @@ __device__ __forceinline__ void deposit_particle_global(const DepositParams &P, 
     }
 }
 
-template <int ND, int S, bool W>
+template <int ND, int S, bool W, bool F>
 __global__ void __launch_bounds__(kThreads) k_deposit_global(const DepositParams P, const TileConfig *gate) {
     if (gate != nullptr && gate->mode != kModeRows) return;
     const int64_t nthreads = (int64_t)gridDim.x * kThreads;
     int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
-    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2], sw = P.stride[3];
+    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2];
+    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2];
     // main loop: kUnroll particles per thread with all loads issued before any use
     for (; i + (kUnroll - 1) * nthreads < P.n; i += kUnroll * nthreads) {
         double x[kUnroll], y[kUnroll], z[kUnroll], w[kUnroll];
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kThreads) k_deposit_global(const DepositParams
             x[u] = ld_stream(px + k * sx);
             y[u] = ND >= 2 ? ld_stream(py + k * sy) : 0.0;
             z[u] = ND >= 3 ? ld_stream(pz + k * sz) : 0.0;
-            w[u] = W ? ld_stream(pw + k * sw) : 1.0;
+            w[u] = W ? particle_weight<F>(P, k) : 1.0;
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) deposit_particle_global<ND, S, W>(P, x[u], y[u], z[u], w[u]);
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreads) k_deposit_global(const DepositParams
         const double x = ld_stream(px + i * sx);
         const double y = ND >= 2 ? ld_stream(py + i * sy) : 0.0;
         const double z = ND >= 3 ? ld_stream(pz + i * sz) : 0.0;
-        const double w = W ? ld_stream(pw + i * sw) : 1.0;
+        const double w = W ? particle_weight<F>(P, i) : 1.0;
         deposit_particle_global<ND, S, W>(P, x, y, z, w);
     }
 }
@@ -129,7 +129,7 @@ template <int ND, int S> struct RowsCfg {
     static constexpr int ITERS = ROWS * G;
 };
 
-template <int ND, int S, bool W, bool STAG>
+template <int ND, int S, bool W, bool STAG, bool F>
 __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P, const TileConfig *gate) {
     if (gate != nullptr && gate->mode != kModeRows) return;
     using C = RowsCfg<ND, S>;
@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
     double *stage = stage_all + warp * C::K * C::KS;
     const int g = lane / C::G, j = lane % C::G;
 
-    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
-    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2], sw = P.stride[3];
+    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2];
+    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2];
     // geometry of the array the reductions go to: the padded grid itself, or the staggered staging grid
     const int pitch = STAG ? P.stag_pitch : P.dims[ND - 1];
     const int row_stride = ND == 1 ? 0 : pitch;                      // between rows of a slab
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
             const double x = ld_stream(px + i * sx);
             const double y = ND >= 2 ? ld_stream(py + i * sy) : 0.0;
             const double z = ND >= 3 ? ld_stream(pz + i * sz) : 0.0;
-            if (W) w = ld_stream(pw + i * sw);
+            if (W) w = particle_weight<F>(P, i);
             ok = shape_axis<S, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], bx, wx);
             if (ND >= 2) ok = shape_axis<S, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], by, wy) && ok;
             if (ND >= 3) ok = shape_axis<S, (S == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], bz, wz) && ok;
@@ -248,7 +248,8 @@ static cudaError_t launch_global(const DepositParams &P, const TileConfig *gate,
     int64_t cap = (int64_t)sm_count * 8;                  // 8 x 256 threads = full occupancy
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
-    k_deposit_global<ND, S, W><<<blocks, kThreads, 0, st>>>(P, gate);
+    if (W && P.fuse_kind) k_deposit_global<ND, S, W, W><<<blocks, kThreads, 0, st>>>(P, gate);
+    else k_deposit_global<ND, S, W, false><<<blocks, kThreads, 0, st>>>(P, gate);
     return cudaGetLastError();
 }
 
@@ -261,7 +262,8 @@ static cudaError_t launch_rows(const DepositParams &P, const TileConfig *gate, i
     if (blocks < 1) blocks = 1;
     if (P.stag != nullptr) {
         if constexpr (S == 1 || S == 2) {
-            k_deposit_rows<ND, S, W, true><<<blocks, kThreads, 0, st>>>(P, gate);
+            if (W && P.fuse_kind) k_deposit_rows<ND, S, W, true, W><<<blocks, kThreads, 0, st>>>(P, gate);
+            else k_deposit_rows<ND, S, W, true, false><<<blocks, kThreads, 0, st>>>(P, gate);
             const int last = P.dims[ND - 1];
             const int64_t rows = (int64_t)P.dims[0] * P.dims[1] * P.dims[2] / last;
             int64_t mb = (rows * last + 255) / 256;
@@ -269,13 +271,14 @@ static cudaError_t launch_rows(const DepositParams &P, const TileConfig *gate, i
             return cudaGetLastError();
         }
     }
-    k_deposit_rows<ND, S, W, false><<<blocks, kThreads, 0, st>>>(P, gate);
+    if (W && P.fuse_kind) k_deposit_rows<ND, S, W, false, W><<<blocks, kThreads, 0, st>>>(P, gate);
+    else k_deposit_rows<ND, S, W, false, false><<<blocks, kThreads, 0, st>>>(P, gate);
     return cudaGetLastError();
 }
 
 template <int ND, int S>
 static cudaError_t dispatch_w(const DepositParams &P, bool rows, const TileConfig *gate, int sm_count, cudaStream_t st) {
-    const bool weighted = P.p[3] != nullptr;
+    const bool weighted = P.p[3] != nullptr || P.fuse_kind != 0;
     if (rows) {
         if constexpr (S >= 1) {
             return weighted ? launch_rows<ND, S, true>(P, gate, sm_count, st) : launch_rows<ND, S, false>(P, gate, sm_count, st);

@@ -58,7 +58,7 @@ template <int ND, int S, int WD> struct RunsMinBlocks {
     static constexpr int value = MV <= 9 ? 4 : MV <= 16 ? 3 : 2;
 };
 
-template <int ND, int S, bool W, bool VEC, int WD>
+template <int ND, int S, bool W, bool VEC, int WD, bool F>
 __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposit_runs(const DepositParams P, const TileConfig *gate) {
     if (gate != nullptr && gate->mode != (WD ? kModeRunsWide : kModeRuns)) return;
     constexpr int NW = StencilWidth<S>::value;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
                 load_k<VEC>(P.p[0], P.stride[0], i0, x);
                 if (ND >= 2) load_k<VEC>(P.p[1], P.stride[1], i0, y);
                 if (ND >= 3) load_k<VEC>(P.p[2], P.stride[2], i0, z);
-                if (W) load_k<VEC>(P.p[3], P.stride[3], i0, w);
+                if (W && (!F || P.p[3])) load_k<VEC>(P.p[3], P.stride[3], i0, w);
             } else {
 #pragma unroll
                 for (int j = 0; j < kRK; ++j) {
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
                     x[j] = in ? P.p[0][(i0 + j) * P.stride[0]] : 0.0;
                     if (ND >= 2) y[j] = in ? P.p[1][(i0 + j) * P.stride[1]] : 0.0;
                     if (ND >= 3) z[j] = in ? P.p[2][(i0 + j) * P.stride[2]] : 0.0;
-                    if (W) w[j] = in ? P.p[3][(i0 + j) * P.stride[3]] : 0.0;
+                    if (W && (!F || P.p[3])) w[j] = in ? P.p[3][(i0 + j) * P.stride[3]] : 0.0;
                 }
             }
         };
@@ -125,6 +125,15 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
             if (i0 >= end) break;
             load_batch(i0);
             const int valid = i0 + kRK <= end ? kRK : (int)(end - i0);      // particles of this batch that exist
+            if constexpr (F) {
+                if (!P.p[3]) {
+#pragma unroll
+                    for (int j = 0; j < kRK; ++j) w[j] = 1.0;
+                }
+#pragma unroll
+                for (int j = 0; j < kRK; ++j)
+                    if (j < valid) w[j] = __dmul_rn(w[j], fused_factor(P, i0 + j));
+            }
 #pragma unroll
             for (int j = 0; j < kRK; ++j) {
                 int b[3] = {0, 0, 0};
@@ -241,7 +250,7 @@ static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, b
     if (P.n <= 0) return cudaSuccess;
     bool vec = true;
     for (int k = 0; k < 4; ++k) {
-        const bool used = k < ND || (k == 3 && W);
+        const bool used = k < ND || (k == 3 && W && P.p[3] != nullptr);
         if (!used) continue;
         if (P.stride[k] != 1 || (reinterpret_cast<uintptr_t>(P.p[k]) & 31u)) vec = false;
     }
@@ -251,19 +260,29 @@ static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, b
     if (blocks < 1) blocks = 1;
     if (wide) {
         if constexpr (WideOk<ND, S>::value) {
-            if (vec) k_deposit_runs<ND, S, W, true, 1><<<blocks, kRT, 0, st>>>(P, gate);
-            else k_deposit_runs<ND, S, W, false, 1><<<blocks, kRT, 0, st>>>(P, gate);
+            if (W && P.fuse_kind) {
+                if (vec) k_deposit_runs<ND, S, W, true, 1, W><<<blocks, kRT, 0, st>>>(P, gate);
+                else k_deposit_runs<ND, S, W, false, 1, W><<<blocks, kRT, 0, st>>>(P, gate);
+            } else {
+                if (vec) k_deposit_runs<ND, S, W, true, 1, false><<<blocks, kRT, 0, st>>>(P, gate);
+                else k_deposit_runs<ND, S, W, false, 1, false><<<blocks, kRT, 0, st>>>(P, gate);
+            }
         }
         return cudaGetLastError();      // (no widened instance for this stencil: nothing launched)
     }
-    if (vec) k_deposit_runs<ND, S, W, true, 0><<<blocks, kRT, 0, st>>>(P, gate);
-    else k_deposit_runs<ND, S, W, false, 0><<<blocks, kRT, 0, st>>>(P, gate);
+    if (W && P.fuse_kind) {
+        if (vec) k_deposit_runs<ND, S, W, true, 0, W><<<blocks, kRT, 0, st>>>(P, gate);
+        else k_deposit_runs<ND, S, W, false, 0, W><<<blocks, kRT, 0, st>>>(P, gate);
+    } else {
+        if (vec) k_deposit_runs<ND, S, W, true, 0, false><<<blocks, kRT, 0, st>>>(P, gate);
+        else k_deposit_runs<ND, S, W, false, 0, false><<<blocks, kRT, 0, st>>>(P, gate);
+    }
     return cudaGetLastError();
 }
 
 template <int ND, int S>
 static cudaError_t runs_w(const DepositParams &P, const TileConfig *gate, bool wide, int sm, cudaStream_t st) {
-    return P.p[3] ? launch_runs<ND, S, true>(P, gate, wide, sm, st) : launch_runs<ND, S, false>(P, gate, wide, sm, st);
+    return (P.p[3] || P.fuse_kind) ? launch_runs<ND, S, true>(P, gate, wide, sm, st) : launch_runs<ND, S, false>(P, gate, wide, sm, st);
 }
 
 template <int ND>

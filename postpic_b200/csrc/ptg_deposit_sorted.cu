@@ -72,7 +72,7 @@ constexpr uint32_t kLongSegment = 2048;     // segments longer than this get a w
 // LONG = true : one CTA (8 warps) per base cell for the longer segments of clustered input: the
 //               segment is cut into 8 equal contiguous parts, one per warp, and the 8 partial
 //               totals are added in warp order -- still a fixed summation order.
-template <int ND, int S, bool W, bool LONG>
+template <int ND, int S, bool W, bool LONG, bool F>
 __global__ void __launch_bounds__(256) k_segment_reduce(const DepositParams P, const uint32_t *idx,
                                                          const uint32_t *off, int cx, int cy, int cz) {
     constexpr int NW = StencilWidth<S>::value;
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) k_segment_reduce(const DepositParams P, c
             const double x = P.p[0][i * P.stride[0]];
             const double y = ND >= 2 ? P.p[1][i * P.stride[1]] : 0.0;
             const double z = ND >= 3 ? P.p[2][i * P.stride[2]] : 0.0;
-            const double w = W ? P.p[3][i * P.stride[3]] : 1.0;
+            const double w = W ? particle_weight<F>(P, i) : 1.0;
             double wx[NW], wy[NW], wz[NW];
             int b0, b1, b2;
             if constexpr (S == 0) {
@@ -232,17 +232,19 @@ static cudaError_t run_sorted(const DepositParams &P, void *ws, size_t ws_bytes,
                 if (ncell <= 0) continue;
                 int64_t wantb = (ncell + 7) / 8;                  // 8 warps per CTA
                 int nb = (int)(wantb < cap * 4 ? wantb : cap * 4);
-                k_segment_reduce<ND, S, W, false><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
+                if (W && P.fuse_kind) k_segment_reduce<ND, S, W, false, W><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
+                else k_segment_reduce<ND, S, W, false, false><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
                 // the long segments of the same colour (clustered input), one CTA each
                 nb = (int)(ncell < cap ? ncell : cap);
-                k_segment_reduce<ND, S, W, true><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
+                if (W && P.fuse_kind) k_segment_reduce<ND, S, W, true, W><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
+                else k_segment_reduce<ND, S, W, true, false><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
             }
     return cudaGetLastError();
 }
 
 template <int ND, int S>
 static cudaError_t sorted_w(const DepositParams &P, void *ws, size_t wsb, int sm, cudaStream_t st) {
-    return P.p[3] ? run_sorted<ND, S, true>(P, ws, wsb, sm, st) : run_sorted<ND, S, false>(P, ws, wsb, sm, st);
+    return (P.p[3] || P.fuse_kind) ? run_sorted<ND, S, true>(P, ws, wsb, sm, st) : run_sorted<ND, S, false>(P, ws, wsb, sm, st);
 }
 
 template <int ND>

@@ -233,7 +233,7 @@ __device__ __forceinline__ void flush_tile(double *tile, const Window &wd, const
     }
 }
 
-template <int ND, int S, bool W, int TT>
+template <int ND, int S, bool W, int TT, bool F>
 __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, const TileConfig *cfgp) {
     extern __shared__ double tile[];
     __shared__ long long scratch[34];
@@ -270,8 +270,8 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
     const int64_t begin = (int64_t)blockIdx.x * per;
     const int64_t end = begin + per < P.n ? begin + per : P.n;
     const int lane = threadIdx.x & 31;
-    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
-    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2], sw = P.stride[3];
+    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2];
+    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2];
 
     // software pipeline: the raw values of the next sub-chunk are in flight while this one is deposited
     double nx = 0, ny = 0, nz = 0, nwt = 1.0;
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
             nx = ld_stream(px + i * sx);
             if (ND >= 2) ny = ld_stream(py + i * sy);
             if (ND >= 3) nz = ld_stream(pz + i * sz);
-            if (W) nwt = ld_stream(pw + i * sw);
+            if (W) nwt = particle_weight<F>(P, i);
         }
     }
     int since_eval = kEvalEvery - 1;       // first evaluation right after the first sub-chunk
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
                 nx = ld_stream(px + j * sx);
                 if (ND >= 2) ny = ld_stream(py + j * sy);
                 if (ND >= 3) nz = ld_stream(pz + j * sz);
-                if (W) nwt = ld_stream(pw + j * sw);
+                if (W) nwt = particle_weight<F>(P, j);
             }
         }
         // ---- stencil in registers --------------------------------------------------
@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
 constexpr int kST = 1024;     // threads per CTA, one CTA per SM
 constexpr int kSU = 4;        // particles in flight per thread
 
-template <int ND, int S, bool W>
+template <int ND, int S, bool W, bool F>
 __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P, const TileConfig *gate) {
     if (gate != nullptr && gate->mode != kModeTiled) return;
     extern __shared__ double tile[];
@@ -508,8 +508,8 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
 
     const int64_t nthreads = (int64_t)gridDim.x * kST;
     int64_t i = (int64_t)blockIdx.x * kST + threadIdx.x;
-    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2], *pw = P.p[3];
-    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2], sw = P.stride[3];
+    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2];
+    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2];
     for (; i + (kSU - 1) * nthreads < P.n; i += kSU * nthreads) {
         double x[kSU], y[kSU], z[kSU], w[kSU];
 #pragma unroll
@@ -518,14 +518,14 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
             x[u] = ld_stream(px + k * sx);
             y[u] = ND >= 2 ? ld_stream(py + k * sy) : 0.0;
             z[u] = ND >= 3 ? ld_stream(pz + k * sz) : 0.0;
-            w[u] = W ? ld_stream(pw + k * sw) : 1.0;
+            w[u] = W ? particle_weight<F>(P, k) : 1.0;
         }
 #pragma unroll
         for (int u = 0; u < kSU; ++u) one(x[u], y[u], z[u], w[u]);
     }
     for (; i < P.n; i += nthreads)
         one(ld_stream(px + i * sx), ND >= 2 ? ld_stream(py + i * sy) : 0.0, ND >= 3 ? ld_stream(pz + i * sz) : 0.0,
-            W ? ld_stream(pw + i * sw) : 1.0);
+            W ? particle_weight<F>(P, i) : 1.0);
     __syncthreads();
     for (int c = threadIdx.x; c < cells; c += kST) {
         double v;
@@ -548,7 +548,8 @@ template <int ND, int S, bool W>
 static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int force, int sm_count, cudaStream_t st) {
     constexpr int NW = StencilWidth<S>::value;
     constexpr int TT = TileThreads<(ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW)>::value;
-    auto kern = k_deposit_tiled<ND, S, W, TT>;
+    const bool fuse = W && P.fuse_kind != 0;
+    auto kern = fuse ? k_deposit_tiled<ND, S, W, TT, W> : k_deposit_tiled<ND, S, W, TT, false>;
     const size_t smem = (size_t)kTileCells * sizeof(double);
     // per-device attribute, cheap to set: done on every launch so that any device works
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -556,7 +557,7 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
     k_probe<ND, S><<<kProbeBlocks, kTT, 0, st>>>(P, cfg, force, runs_wide_available(ND, S) ? 1 : 0);
     if ((int64_t)P.dims[0] * P.dims[1] * P.dims[2] <= kTileCells) {
         // the whole padded grid fits the tile: lean kernel without window management
-        auto small = k_deposit_small<ND, S, W>;
+        auto small = fuse ? k_deposit_small<ND, S, W, W> : k_deposit_small<ND, S, W, false>;
         e = cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int64_t want = (P.n + (int64_t)kST * kSU - 1) / ((int64_t)kST * kSU);
@@ -569,7 +570,7 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
 
 template <int ND, int S>
 static cudaError_t tiled_w(const DepositParams &P, TileConfig *cfg, int force, int sm, cudaStream_t st) {
-    return P.p[3] ? launch_tiled<ND, S, true>(P, cfg, force, sm, st) : launch_tiled<ND, S, false>(P, cfg, force, sm, st);
+    return (P.p[3] || P.fuse_kind) ? launch_tiled<ND, S, true>(P, cfg, force, sm, st) : launch_tiled<ND, S, false>(P, cfg, force, sm, st);
 }
 
 template <int ND>

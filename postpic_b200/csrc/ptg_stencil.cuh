@@ -116,6 +116,12 @@ struct DepositParams {
     double *stag;
     int stag_pitch;
     int64_t stag_copy;      // distance between the two copies, in doubles
+    // fused kinetic weight (0 = off): the particle's weight is weight[i] (or 1) times a scalar of
+    // its momentum, evaluated in the kernel instead of in a separate pass
+    int fuse_kind;
+    const double *q[3];     // px, py, pz
+    int64_t qstride[3];
+    double f_mass, f_mc2, f_c2, f_qe;   // mass, (mass*c)^2, c^2, elementary charge
 };
 
 // Streaming 8-byte load: read-only path, do not allocate in L1 and mark the line evict-first
@@ -131,6 +137,40 @@ __device__ __forceinline__ double ld_stream(const double *p) {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
+}
+
+// The kinetic scalars of postpic's default scalar context (scalarproperties.py:183-205) in the order
+// the nested expressions prescribe: _np2 = (px**2+py**2+pz**2)/(mass*c)**2, gamma_m1 = _np2/(sqrt(1+_np2)+1),
+// Ekin = gamma_m1*mass*c**2, Ekin_MeV = Ekin/elementary_charge/1e6.  kind: PTG_W_* of ptg_b200.h.
+__device__ __forceinline__ double kinetic_value(int kind, double x, double y, double z, double mass, double mc2,
+                                                double c2, double qe) {
+    const double p2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+    if (kind == 6) return sqrt(p2);                                        // p
+    const double np2 = p2 / mc2;
+    const double gm1 = np2 / __dadd_rn(sqrt(__dadd_rn(1.0, np2)), 1.0);
+    switch (kind) {
+        case 1: return gm1;                                                // gamma_m1
+        case 2: return __dadd_rn(gm1, 1.0);                                // gamma
+        case 3: return __dmul_rn(__dmul_rn(gm1, mass), c2);                // Ekin [J]
+        case 4: return __dmul_rn(__dmul_rn(gm1, mass), c2) / qe / 1e6;     // Ekin_MeV
+        default: return __dmul_rn(__dmul_rn(gm1, mass), c2) / qe / 1e3;    // Ekin_keV
+    }
+}
+
+// Weight of particle i for the weighted kernels: the weights array (1 when absent), times the fused
+// kinetic scalar when one is requested.
+__device__ __forceinline__ double fused_factor(const DepositParams &P, int64_t i) {
+    return kinetic_value(P.fuse_kind, __ldg(P.q[0] + i * P.qstride[0]), __ldg(P.q[1] + i * P.qstride[1]),
+                         __ldg(P.q[2] + i * P.qstride[2]), P.f_mass, P.f_mc2, P.f_c2, P.f_qe);
+}
+// F = false is the plain weighted kernel (the weights array exists); F = true instantiates the fused
+// variants, whose weights array is optional.  A template flag, not a run-time one: the fused code
+// costs the plain kernels no register.
+template <bool F>
+__device__ __forceinline__ double particle_weight(const DepositParams &P, int64_t i) {
+    if (!F) return ld_stream(P.p[3] + i * P.stride[3]);
+    const double w = P.p[3] ? ld_stream(P.p[3] + i * P.stride[3]) : 1.0;
+    return __dmul_rn(w, fused_factor(P, i));
 }
 
 // Fire-and-forget fp64 reduction into global memory: a single native

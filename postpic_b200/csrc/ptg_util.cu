@@ -110,21 +110,7 @@ __global__ void __launch_bounds__(256) k_weights(int kind, int64_t n, const doub
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
         const double x = ld_stream(px + i * s0), y = ld_stream(py + i * s1), z = ld_stream(pz + i * s2);
-        const double p2 = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
-        double v;
-        if (kind == 6) {
-            v = sqrt(p2);                                                   // p
-        } else {
-            const double np2 = p2 / mc2;
-            const double gm1 = np2 / __dadd_rn(sqrt(__dadd_rn(1.0, np2)), 1.0);
-            switch (kind) {
-                case 1: v = gm1; break;                                                     // gamma_m1
-                case 2: v = __dadd_rn(gm1, 1.0); break;                                     // gamma
-                case 3: v = __dmul_rn(__dmul_rn(gm1, mass), c2); break;                     // Ekin [J]
-                case 4: v = __dmul_rn(__dmul_rn(gm1, mass), c2) / qe / 1e6; break;          // Ekin_MeV
-                default: v = __dmul_rn(__dmul_rn(gm1, mass), c2) / qe / 1e3; break;         // Ekin_keV
-            }
-        }
+        const double v = kinetic_value(kind, x, y, z, mass, mc2, c2, qe);
         out[i] = weight ? __dmul_rn(ld_stream(weight + i * s3), v) : v;
     }
 }

@@ -63,10 +63,13 @@ class Plan(object):
         return float(np.prod([e[1] - e[0] for e in self.edges]))
 
 
-def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, stream=None):
+def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, stream=None, fused=None):
     """Deposit CUDA tensors `coords` (+ optional `weights`) into the padded CUDA tensor `grid`.
 
-    Asynchronous on `stream` (default: torch's current stream on grid.device)."""
+    Asynchronous on `stream` (default: torch's current stream on grid.device).
+    `fused` = dict(kind=, px=, py=, pz=, mass=[, c=, elementary_charge=]) multiplies every particle's
+    weight by a kinetic scalar of its momentum inside the deposit kernel (ptg_deposit_fused_f64):
+    `weights='Ekin_MeV'` of createField without materialising a weights array."""
     torch = _torch()
     lib = _lib.load()
     if len(coords) != plan.ndim:
@@ -92,13 +95,27 @@ def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, strea
     flags = _lib.METHODS[method] | (_lib.ZERO_GRID if zero else 0)
     with torch.cuda.device(grid.device):
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
-        _lib.check(lib.ptg_deposit_f64(plan.ndim, plan.shape, n, ptr[0], ptr[1], ptr[2], ptr[3], cstr,
-                                       plan.lo.ctypes.data, plan.inv.ctypes.data, plan.cbins,
-                                       grid.data_ptr(), flags, None, 0, st))
+        if fused is None:
+            _lib.check(lib.ptg_deposit_f64(plan.ndim, plan.shape, n, ptr[0], ptr[1], ptr[2], ptr[3], cstr,
+                                           plan.lo.ctypes.data, plan.inv.ctypes.data, plan.cbins,
+                                           grid.data_ptr(), flags, None, 0, st))
+        else:
+            q = [fused['px'], fused['py'], fused['pz']]
+            for t, nm in zip(q, ('px', 'py', 'pz')):
+                _check_tensor(t, nm)
+                if t.numel() < n or t.device != grid.device:
+                    raise ValueError('fused momentum arrays must match the coordinates')
+            qstr = (ctypes.c_int64 * 3)(*[t.stride(0) if n > 1 else 1 for t in q])
+            _lib.check(lib.ptg_deposit_fused_f64(
+                plan.ndim, plan.shape, n, ptr[0], ptr[1], ptr[2], ptr[3], cstr, plan.lo.ctypes.data,
+                plan.inv.ctypes.data, plan.cbins, grid.data_ptr(), flags, WEIGHT_KINDS[fused['kind']],
+                q[0].data_ptr() if n else None, q[1].data_ptr() if n else None, q[2].data_ptr() if n else None, qstr,
+                float(fused['mass']), float(fused.get('c', 299792458.0)),
+                float(fused.get('elementary_charge', 1.602176634e-19)), st))
     return grid
 
 
-def deposit(coords, weights=None, range=None, bins=None, shape=0, method=None):
+def deposit(coords, weights=None, range=None, bins=None, shape=0, method=None, fused=None):
     """-> (padded grid CUDA tensor, plan).  `plan.interior` slices out the histogram."""
     torch = _torch()
     coords = list(coords)
@@ -107,7 +124,7 @@ def deposit(coords, weights=None, range=None, bins=None, shape=0, method=None):
         range = [range]
     plan = Plan(range, as_bins(bins[0] if (nd == 1 and np.ndim(bins)) else bins, nd), shape)
     grid = torch.empty(plan.dims, dtype=torch.float64, device=coords[0].device)
-    deposit_into(grid, plan, coords, weights, method=method, zero=True)
+    deposit_into(grid, plan, coords, weights, method=method, zero=True, fused=fused)
     return grid, plan
 
 

@@ -263,17 +263,22 @@ class MultiSpecies(object):
             return _device._torch().cat(parts)
         return np.hstack(parts)
 
+    def _fusable(self, weights):
+        """The extra weight is a kinetic scalar that the CUDA kernels can evaluate themselves."""
+        key = getattr(weights, 'symbol', weights)
+        ok = (isinstance(key, str) and key in _device.WEIGHT_KINDS and bool(self._sources) and
+              all(s.device is not None and all(_device.is_cuda_tensor(s._arrays.get(k)) for k in ('px', 'py', 'pz'))
+                  and s._arrays.get('mass', None) is not None and np.ndim(s._arrays.get('mass')) == 0
+                  for s in self._sources))
+        return key if ok else None
+
     def _weights(self, weights):
         """`weight * (weights)` per particle (particles.py:1097).  Device-resident species whose extra
         weight is one of the kinetic scalars (gamma, gamma_m1, Ekin, Ekin_MeV, Ekin_keV, p) are evaluated
         by one fused CUDA pass over px, py, pz, weight (ptg_weights_f64) instead of the chain of
         expression temporaries; everything else goes through the generic evaluator."""
-        key = getattr(weights, 'symbol', weights)
-        fusable = (isinstance(key, str) and key in _device.WEIGHT_KINDS and self._sources and
-                   all(s.device is not None and all(_device.is_cuda_tensor(s._arrays.get(k)) for k in ('px', 'py', 'pz'))
-                       and np.ndim(s._arrays.get('mass', None)) == 0 and s._arrays.get('mass', None) is not None
-                       for s in self._sources))
-        if not fusable:
+        key = self._fusable(weights)
+        if key is None:
             return self('weight * ({})'.format(weights))
         parts = []
         for s in self._sources:
@@ -335,7 +340,7 @@ class MultiSpecies(object):
             edges = [edges_of(r, bins[i]) for i, r in zip(range(h.ndim), ranges)]
             return h, edges
 
-        if len(self._sources) > 1 and all(s.device is not None for s in self._sources):
+        if all(s.device is not None for s in self._sources):
             return self._createHistgram_per_species(sps, ranges, weights, bins, shape)
         w = self._weights(weights)
         h, edges = histogramdd(data, weights=w, range=ranges, bins=bins, shape=shape)
@@ -352,15 +357,37 @@ class MultiSpecies(object):
         from ._routines import _DEFAULT_BINS
         torch = _device._torch()
         nd = len(sps)
-        singles = [MultiSpecies(s) for s in self._sources]
-        per = [([m(sp) for sp in sps], m._weights(weights)) for m in singles if len(m) > 0]
-        per = [(d if all(_device.is_cuda_tensor(a) for a in d) else [torch.as_tensor(np.asarray(a), device=self._sources[0].device) for a in d], w) for d, w in per]
+        singles = [MultiSpecies(s) for s in self._sources if len(s) > 0]
+        dev = self._sources[0].device
+        c = _sc.c if _sc is not None else _CONSTANTS['c']
+        qe = _sc.elementary_charge if _sc is not None else _CONSTANTS['elementary_charge']
+        per = []            # (axis data, weights array or None, fused spec or None) per species
+        for m in singles:
+            d = [m(sp) for sp in sps]
+            d = [a if _device.is_cuda_tensor(a) else torch.as_tensor(np.asarray(a, dtype='float64'), device=dev)
+                 for a in d]
+            src = m._sources[0]
+            kind = m._fusable(weights)
+            if kind is not None:
+                # weight * <kinetic scalar> is evaluated inside the deposit kernels (ptg_deposit_fused_f64)
+                wt = src._arrays.get('weight', 1.0)
+                if _device.is_cuda_tensor(wt):
+                    w = wt
+                elif float(wt) == 1.0:
+                    w = None
+                else:
+                    w = torch.full((len(src),), float(wt), dtype=torch.float64, device=dev)
+                fused = dict(kind=kind, px=src._arrays['px'], py=src._arrays['py'], pz=src._arrays['pz'],
+                             mass=float(src._arrays['mass']), c=c, elementary_charge=qe)
+            else:
+                w, fused = m._weights(weights), None
+            per.append((d, w, fused))
         rng = []
         for a in range(nd):
             r = ranges[a]
             lo, hi = (None, None) if r is None else (r[0], r[1])
             if lo is None or hi is None:
-                mm = [_device.minmax(d[a].contiguous() if d[a].stride(0) < 1 else d[a]) for d, _ in per]
+                mm = [_device.minmax(d[a].contiguous() if d[a].stride(0) < 1 else d[a]) for d, _, _ in per]
                 lo = min(m[0] for m in mm) if lo is None else lo
                 hi = max(m[1] for m in mm) if hi is None else hi
             rng.append((lo, hi))
@@ -370,9 +397,10 @@ class MultiSpecies(object):
             bins = (bins,) * nd
         plan = _device.Plan(rng, as_bins(bins[0] if nd == 1 else bins, nd), 2 if shape is None else shape)
         grid = torch.zeros(plan.dims, dtype=torch.float64, device=self._sources[0].device)
-        for d, w in per:
+        for d, w, fused in per:
             _device.deposit_into(grid, plan, [t if t.dtype == torch.float64 else t.to(torch.float64) for t in d],
-                                 w if (w is None or w.dtype == torch.float64) else w.to(torch.float64), zero=False)
+                                 w if (w is None or w.dtype == torch.float64) else w.to(torch.float64), zero=False,
+                                 fused=fused)
         _device.scale_(grid, 1.0 / plan.cell_volume())
         h = grid.cpu().numpy()[plan.interior]
         return h, tuple(plan.edges)

@@ -222,6 +222,34 @@ class TestCreateField:
                                      elementary_charge=sc.elementary_charge).cpu().numpy()
         assert np.allclose(got, expect[::2], rtol=1e-14, atol=0)
 
+    @pytest.mark.parametrize("method", [None, 'rows', 'global', 'tiled', 'runs', 'runs_wide', 'sorted'])
+    def test_fused_deposit_equals_two_step(self, method):
+        """ptg_deposit_fused_f64 (kinetic weight evaluated inside the deposit kernels) against
+        ptg_weights_f64 followed by ptg_deposit_f64, for every method, on random and cell-ordered input."""
+        import scipy.constants as sc
+        import torch
+        from postpic_b200 import device
+        n = 3_000_000
+        g = torch.Generator(device='cuda').manual_seed(8)
+        x = torch.rand(n, dtype=torch.float64, device='cuda', generator=g) * 1.02 - 0.01
+        y = torch.rand(n, dtype=torch.float64, device='cuda', generator=g) * 1.02 - 0.01
+        me = 9.109383e-31
+        px, py, pz = (torch.randn(n, dtype=torch.float64, device='cuda', generator=g) * me * sc.c for _ in range(3))
+        wt = torch.rand(n, dtype=torch.float64, device='cuda', generator=g) + 0.5
+        order = torch.argsort((x.clamp(0, 1) * 200).floor() * 200 + (y.clamp(0, 1) * 200).floor())
+        for idx in (None, order):
+            sel = (lambda t: t) if idx is None else (lambda t: t[idx].contiguous())
+            for shape in (1, 2) if method != 'runs_wide' else (1,):
+                for w_arr in (sel(wt), None):
+                    fused = dict(kind='Ekin_MeV', px=sel(px), py=sel(py), pz=sel(pz), mass=me, c=sc.c,
+                                 elementary_charge=sc.elementary_charge)
+                    kw = dict(range=[(0, 1), (0, 1)], bins=(200, 200), shape=shape)
+                    got, _ = device.deposit([sel(x), sel(y)], w_arr, method=method, fused=fused, **kw)
+                    w2 = device.kinetic_weights('Ekin_MeV', fused['px'], fused['py'], fused['pz'], w_arr, mass=me,
+                                                c=sc.c, elementary_charge=sc.elementary_charge)
+                    ref, _ = device.deposit([sel(x), sel(y)], w2, method='global', **kw)
+                    assert float((got - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+
     def test_multi_species_on_device_deposits_without_concatenation(self):
         from postpic_b200 import MultiSpecies, ArraySource
         import torch
