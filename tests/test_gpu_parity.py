@@ -485,3 +485,56 @@ def test_no_write_outside_the_padded_grid(nd, shape, method):
         torch.cuda.synchronize()
         assert not buf[:guard].any() and not buf[guard + plan.cells:].any()
         assert torch.isfinite(grid).all()
+
+
+def test_randomised_differential_against_oracle(ptg, oracle):
+    """400 random problems (dimension, shape, weights or not, 1..48 bins per axis, forward / reversed /
+    tiny / huge ranges, 0..5000 particles that overshoot the range, NaN and inf sprinkled in, every
+    deposition method) -- CUDA path vs oracle, padded grids and edges."""
+    rng = np.random.default_rng(20240607)
+    checked = 0
+    for trial in range(400):
+        nd = int(rng.integers(1, 4))
+        shape = int(rng.integers(0, 4))
+        weighted = bool(rng.integers(0, 2))
+        method = METHODS[int(rng.integers(0, len(METHODS)))]
+        if method == 'runs_wide' and ((1 if shape == 0 else shape + 1) + 1) ** nd > 27:
+            method = 'runs'
+        n = int(rng.choice([0, 1, 2, 31, 33, 257, 1000, 5000]))
+        bins = [int(rng.integers(1, 49)) for _ in range(nd)]
+        ranges, coords = [], []
+        for a in range(nd):
+            kind = rng.integers(0, 5)
+            lo = float(rng.normal(0, 10))
+            span = float(10.0 ** rng.uniform(-6, 6))
+            hi = lo + span
+            if kind == 0:
+                lo, hi = hi, lo                               # reversed range
+            elif kind == 1:
+                lo, hi, span = 0.0, 1.0, 1.0
+            ranges.append((lo, hi))
+            c = rng.uniform(min(lo, hi) - 0.2 * span, max(lo, hi) + 0.2 * span, n)
+            if n > 8:
+                # raw-double-tested axes (y; z for 3-D shape 1) crash the reference for +inf / huge values
+                # (dropped here), so those only go on int-tested axes where the reference is defined
+                c[0] = np.nan
+                c[1] = -np.inf
+                if a == 0 or (a == 2 and shape != 1):
+                    c[2] = np.inf
+                    c[3] = 1e300
+                c[4] = lo
+                c[5] = hi
+            coords.append(c)
+        w = rng.normal(1.0, 2.0, n) if weighted else None
+        ptg.method = method
+        hg, eg = cases.call(ptg, coords, w, shape, ranges=ranges, bins=bins)
+        ho, eo = cases.call(oracle, coords, w, shape, ranges=ranges, bins=bins)
+        a, b = cases.padded(hg), cases.padded(ho)
+        assert a.shape == b.shape, (trial, nd, shape, method)
+        scale = np.max(np.abs(b)) if b.size else 0.0
+        assert np.max(np.abs(a - b), initial=0.0) <= 1e-12 * scale + 1e-300, (trial, nd, shape, weighted, method, n, bins, ranges)
+        for x, y in zip(eg, eo):
+            assert np.array_equal(x, y)
+        checked += 1
+    ptg.method = None
+    assert checked == 400

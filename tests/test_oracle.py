@@ -101,6 +101,38 @@ def test_oracle_matches_reference_bit_exact(oracle, ref, nd, shape, weighted):
         assert np.array_equal(a, b)
 
 
+def test_oracle_randomised_vs_reference_bit_exact(oracle, ref):
+    """300 random problems (reversed / tiny / huge ranges, 1..48 bins, NaN / -inf, values on the edges):
+    the restatement must reproduce the executed reference bit for bit."""
+    if ref is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    rng = np.random.default_rng(777)
+    for trial in range(300):
+        nd = int(rng.integers(1, 4))
+        shape = int(rng.integers(0, 4))
+        n = int(rng.choice([0, 1, 2, 33, 1000, 4000]))
+        bins = [int(rng.integers(1, 49)) for _ in range(nd)]
+        ranges, coords = [], []
+        for a in range(nd):
+            lo = float(rng.normal(0, 10))
+            span = float(10.0 ** rng.uniform(-6, 6))
+            hi = lo + span
+            if rng.integers(0, 4) == 0:
+                lo, hi = hi, lo
+            ranges.append((lo, hi))
+            c = rng.uniform(min(lo, hi) - 0.2 * span, max(lo, hi) + 0.2 * span, n)
+            if n > 8:
+                c[0], c[1], c[4], c[5] = np.nan, -np.inf, lo, hi
+                if a == 0 or (a == 2 and shape != 1):          # +inf / huge are defined on int-tested axes only
+                    c[2], c[3] = np.inf, 1e300
+            coords.append(c)
+        w = rng.normal(1.0, 2.0, n) if rng.integers(0, 2) else None
+        ho, eo = cases.call(oracle, coords, w, shape, ranges=ranges, bins=bins)
+        hr, er = cases.call(ref, coords, w, shape, ranges=ranges, bins=bins)
+        assert np.array_equal(cases.padded(ho), cases.padded(hr), equal_nan=True), (trial, nd, shape, bins, ranges)
+        assert all(np.array_equal(a, b) for a, b in zip(eo, er))
+
+
 def test_oracle_strided_inputs(oracle, ref):
     base = np.random.default_rng(5).uniform(0, 1, (3000, 3))
     cols = [base[:, i] for i in range(3)]
