@@ -294,7 +294,9 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind,
                          "sample": "each step deposits %.3g particles of the workload (single-threaded: the "
                                    "reference holds the GIL and has no threads); %s, %d logical cpus"
-                                   % (sample_n, cpu_model(), os.cpu_count())},
+                                   % (sample_n, cpu_model(), os.cpu_count()),
+                         # what one process per hardware thread on disjoint particle blocks would give
+                         "all_cores": time_cpu_all_cores(name, 4 * sample_n)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
