@@ -62,7 +62,6 @@ template <int ND, int S, bool W, bool VEC, int WD, bool F>
 __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposit_runs(const DepositParams P, const TileConfig *gate) {
     if (gate != nullptr && gate->mode != (WD ? kModeRunsWide : kModeRuns)) return;
     constexpr int NW = StencilWidth<S>::value;
-    constexpr int SS = S == 0 ? 1 : S;
     // register window of the open run: the stencil of its first particle, widened by WD cells per
     // axis so that neighbours whose base cell is one further along any axis still fit
     constexpr int MW = NW + WD;
@@ -136,22 +135,9 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
             }
 #pragma unroll
             for (int j = 0; j < kRK; ++j) {
-                int b[3] = {0, 0, 0};
+                int b[3];
                 double wx[NW], wy[NW], wz[NW];
-                bool ok = j < valid;
-                if constexpr (S == 0) {
-                    ok = ngp_axis(x[j], P.lo[0], P.inv[0], P.fbins[0], b[0]) && ok;
-                    if (ND >= 2) ok = ngp_axis(y[j], P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
-                    if (ND >= 3) ok = ngp_axis(z[j], P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
-                    wx[0] = wy[0] = wz[0] = 1.0;
-                } else {
-                    double (&rx)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wx);
-                    double (&ry)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wy);
-                    double (&rz)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wz);
-                    ok = shape_axis<SS, false>(x[j], P.lo[0], P.inv[0], P.fbins_p1[0], b[0], rx) && ok;
-                    if (ND >= 2) ok = shape_axis<SS, true>(y[j], P.lo[1], P.inv[1], P.fbins_p1[1], b[1], ry) && ok;
-                    if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z[j], P.lo[2], P.inv[2], P.fbins_p1[2], b[2], rz) && ok;
-                }
+                const bool ok = particle_stencil<ND, S>(P, x[j], y[j], z[j], b, wx, wy, wz) && j < valid;
                 if (!ok) continue;
                 const double wj = W ? w[j] : 1.0;
                 if (WD && W && !(fabs(wj) <= 1.79769313486231570e308)) {
@@ -162,10 +148,8 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
                         for (int c = 0; c < (ND >= 2 ? NW : 1); ++c)
 #pragma unroll
                             for (int d = 0; d < (ND >= 3 ? NW : 1); ++d) {
-                                double v = wx[a];
-                                if (ND >= 2) v = __dmul_rn(v, wy[c]);
-                                if (ND >= 3) v = __dmul_rn(v, wz[d]);
-                                red_add(P.grid + (((int64_t)(b[0] + a)) * g1 + (b[1] + c)) * g2 + (b[2] + d), __dmul_rn(v, wj));
+                                red_add(P.grid + (((int64_t)(b[0] + a)) * g1 + (b[1] + c)) * g2 + (b[2] + d),
+                                        stencil_value<ND, S, true>(wx, wy, wz, a, c, d, wj));
                             }
                     continue;
                 }
@@ -200,14 +184,9 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
                     for (int c = 0; c < MC; ++c)
 #pragma unroll
                         for (int d = 0; d < MD; ++d) {
-                            double v;
-                            if (S == 0 && !WD) v = wj;
-                            else if (ND == 1) v = W ? __dmul_rn(sx[a], wj) : sx[a];
-                            else {
-                                v = __dmul_rn(sx[a], sy[c]);
-                                if (ND == 3) v = __dmul_rn(v, sz[d]);
-                                if (W) v = __dmul_rn(v, wj);
-                            }
+                            // (a widened window needs the products also for shape 0: the shifted 1.0 / 0.0)
+                            const double v = WD ? stencil_value<ND, 1, W>(sx, sy, sz, a, c, d, wj)
+                                                : stencil_value<ND, S, W>(sx, sy, sz, a, c, d, wj);
                             const int k = (a * MC + c) * MD + d;
                             acc[k] = __dadd_rn(acc[k], v);
                         }

@@ -29,24 +29,14 @@ namespace ptg {
 template <int ND, int S>
 __global__ void __launch_bounds__(256) k_cell_keys(const DepositParams P, uint32_t cells, uint32_t *keys,
                                                     uint32_t *idx) {
-    constexpr int SS = S == 0 ? 1 : S;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += step) {
         const double x = ld_stream(P.p[0] + i * P.stride[0]);
         const double y = ND >= 2 ? ld_stream(P.p[1] + i * P.stride[1]) : 0.0;
         const double z = ND >= 3 ? ld_stream(P.p[2] + i * P.stride[2]) : 0.0;
-        int b[3] = {0, 0, 0};
-        bool ok;
-        if constexpr (S == 0) {
-            ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], b[0]);
-            if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
-            if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
-        } else {
-            double w[SS + 1];
-            ok = shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b[0], w);
-            if (ND >= 2) ok = shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], b[1], w) && ok;
-            if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b[2], w) && ok;
-        }
+        int b[3];
+        double wx[StencilWidth<S>::value], wy[StencilWidth<S>::value], wz[StencilWidth<S>::value];
+        const bool ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz);
         uint32_t key = cells;
         if (ok) key = (uint32_t)((b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2]);    // dims beyond ndim are 1
         keys[i] = key;
@@ -76,7 +66,6 @@ template <int ND, int S, bool W, bool LONG, bool F>
 __global__ void __launch_bounds__(256) k_segment_reduce(const DepositParams P, const uint32_t *idx,
                                                          const uint32_t *off, int cx, int cy, int cz) {
     constexpr int NW = StencilWidth<S>::value;
-    constexpr int SS = S == 0 ? 1 : S;
     constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
     constexpr int NV = NA * NC * NDD;
     __shared__ double s_part[LONG ? 8 * NV : 1];
@@ -111,32 +100,16 @@ __global__ void __launch_bounds__(256) k_segment_reduce(const DepositParams P, c
             const double z = ND >= 3 ? P.p[2][i * P.stride[2]] : 0.0;
             const double w = W ? particle_weight<F>(P, i) : 1.0;
             double wx[NW], wy[NW], wz[NW];
-            int b0, b1, b2;
-            if constexpr (S == 0) {
-                wx[0] = wy[0] = wz[0] = 1.0;
-            } else {
-                double (&rx)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wx);
-                double (&ry)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wy);
-                double (&rz)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wz);
-                shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b0, rx);
-                if (ND >= 2) shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], b1, ry);
-                if (ND >= 3) shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b2, rz);
-            }
+            int b[3];
+            particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz);      // accepted already: it has a cell key
 #pragma unroll
             for (int a = 0; a < NA; ++a)
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
 #pragma unroll
                     for (int d = 0; d < NDD; ++d) {
-                        double v;
-                        if (S == 0) v = W ? w : 1.0;
-                        else if (ND == 1) v = W ? __dmul_rn(wx[a], w) : wx[a];
-                        else {
-                            v = __dmul_rn(wx[a], wy[c]);
-                            if (ND == 3) v = __dmul_rn(v, wz[d]);
-                            if (W) v = __dmul_rn(v, w);
-                        }
-                        acc[(a * NC + c) * NDD + d] = __dadd_rn(acc[(a * NC + c) * NDD + d], v);
+                        acc[(a * NC + c) * NDD + d] = __dadd_rn(acc[(a * NC + c) * NDD + d],
+                                                                stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w));
                     }
         }
         // fixed-order butterfly: every lane ends with the same total

@@ -49,23 +49,11 @@ __device__ __forceinline__ long long block_sum(long long v, long long *scratch /
     return scratch[32];
 }
 
-// stencil base cell of one particle on every axis (no weights): shared by probe and kernel
+// stencil base cell of one particle on every axis (the weights are discarded): used by the probe
 template <int ND, int S>
 __device__ __forceinline__ bool base_cells(const DepositParams &P, double x, double y, double z, int (&b)[3]) {
-    b[0] = b[1] = b[2] = 0;
-    if (S == 0) {
-        bool ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], b[0]);
-        if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
-        if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
-        return ok;
-    } else {
-        constexpr int SS = S == 0 ? 1 : S;
-        double w[SS + 1];
-        bool ok = shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b[0], w);
-        if (ND >= 2) ok = shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], b[1], w) && ok;
-        if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b[2], w) && ok;
-        return ok;
-    }
+    double wx[StencilWidth<S>::value], wy[StencilWidth<S>::value], wz[StencilWidth<S>::value];
+    return particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz);
 }
 
 // ---------------------------------------------------------------------------------
@@ -240,7 +228,6 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
     __shared__ Window s_win;
     __shared__ unsigned s_acc, s_miss;
     constexpr int NW = StencilWidth<S>::value;
-    constexpr int SS = S == 0 ? 1 : S;
 
     const TileConfig cfg = *cfgp;
     if (cfg.mode != kModeTiled) return;
@@ -299,32 +286,11 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
             }
         }
         // ---- stencil in registers --------------------------------------------------
-        int b[3] = {0, 0, 0};
+        int b[3];
         double wx[NW], wy[NW], wz[NW];
-        bool ok = i < end;
-        if (ok) {
-            if constexpr (S == 0) {
-                ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], b[0]);
-                if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
-                if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
-                wx[0] = wy[0] = wz[0] = 1.0;
-            } else {
-                double (&rx)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wx);
-                double (&ry)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wy);
-                double (&rz)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wz);
-                ok = shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b[0], rx);
-                if (ND >= 2) ok = shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], b[1], ry) && ok;
-                if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b[2], rz) && ok;
-            }
-        }
+        const bool ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) && i < end;
         // value of stencil cell (a, c, d), reference operation order: ((wx*wy)*wz)*w
-        auto value = [&](int a, int c, int d) -> double {
-            if (S == 0) return W ? w : 1.0;
-            if (ND == 1) return W ? __dmul_rn(wx[a], w) : wx[a];
-            double t = __dmul_rn(wx[a], wy[c]);
-            if (ND == 3) t = __dmul_rn(t, wz[d]);
-            return W ? __dmul_rn(t, w) : t;
-        };
+        auto value = [&](int a, int c, int d) -> double { return stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w); };
         constexpr int NV = ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW;
         // stencils of up to 16 cells are materialised so that runs can be summed across the warp;
         // the big 3-D stencils (27, 64 cells) are evaluated on the fly and never aggregated
@@ -446,7 +412,6 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
     if (gate != nullptr && gate->mode != kModeTiled) return;
     extern __shared__ double tile[];
     constexpr int NW = StencilWidth<S>::value;
-    constexpr int SS = S == 0 ? 1 : S;
     constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
     // Plain counting (shape 0, no weights -- numpy.histogram's job): every contribution is exactly 1,
     // so the tile holds 32-bit counters and uses the one NATIVE shared-memory atomic of sm_100a
@@ -466,22 +431,9 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
     const int p1 = ND >= 2 ? P.dims[1] : 1, p2 = ND >= 3 ? P.dims[2] : 1;
 
     auto one = [&](double x, double y, double z, double w) {
-        int b[3] = {0, 0, 0};
+        int b[3];
         double wx[NW], wy[NW], wz[NW];
-        bool ok;
-        if constexpr (S == 0) {
-            ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], b[0]);
-            if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
-            if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
-            wx[0] = wy[0] = wz[0] = 1.0;
-        } else {
-            double (&rx)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wx);
-            double (&ry)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wy);
-            double (&rz)[SS + 1] = reinterpret_cast<double (&)[SS + 1]>(wz);
-            ok = shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b[0], rx);
-            if (ND >= 2) ok = shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], b[1], ry) && ok;
-            if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b[2], rz) && ok;
-        }
+        const bool ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz);
         if (!ok) return;
         if constexpr (COUNT) {
             atomicAdd(cmine + (b[0] * p1 + b[1]) * p2 + b[2], 1u);
@@ -494,15 +446,7 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
             for (int c = 0; c < NC; ++c)
 #pragma unroll
                 for (int d = 0; d < NDD; ++d) {
-                    double v;
-                    if (S == 0) v = W ? w : 1.0;
-                    else if (ND == 1) v = W ? __dmul_rn(wx[a], w) : wx[a];
-                    else {
-                        v = __dmul_rn(wx[a], wy[c]);
-                        if (ND == 3) v = __dmul_rn(v, wz[d]);
-                        if (W) v = __dmul_rn(v, w);
-                    }
-                    atomicAdd(t + (a * p1 + c) * p2 + d, v);
+                    atomicAdd(t + (a * p1 + c) * p2 + d, stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w));
                 }
     };
 

@@ -124,6 +124,42 @@ struct DepositParams {
     double f_mass, f_mc2, f_c2, f_qe;   // mass, (mass*c)^2, c^2, elementary charge
 };
 
+// Stencil of one particle on all axes: accept test, padded base cell b[a] and the per-axis weights
+// (a single 1.0 for shape 0).  Axis kinds as in the reference: x on the truncated int, y on the raw
+// double, z on the raw double only for shape 1.
+template <int ND, int S>
+__device__ __forceinline__ bool particle_stencil(const DepositParams &P, double x, double y, double z, int (&b)[3],
+                                                 double (&wx)[StencilWidth<S>::value],
+                                                 double (&wy)[StencilWidth<S>::value],
+                                                 double (&wz)[StencilWidth<S>::value]) {
+    b[0] = b[1] = b[2] = 0;
+    bool ok;
+    if constexpr (S == 0) {
+        ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], b[0]);
+        if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], b[1]) && ok;
+        if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], b[2]) && ok;
+        wx[0] = wy[0] = wz[0] = 1.0;
+    } else {
+        ok = shape_axis<S, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b[0], wx);
+        if (ND >= 2) ok = shape_axis<S, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], b[1], wy) && ok;
+        if (ND >= 3) ok = shape_axis<S, (S == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], b[2], wz) && ok;
+    }
+    return ok;
+}
+
+// Contribution of a particle to stencil cell (a, c, d) in the reference's operation order:
+// 1-D  stencil*w (pyx:90,:107);  2-D (wx*wy)*w (pyx:211,:244,:276);  3-D ((wx*wy)*wz)*w (pyx:382,:421,:463);
+// shape 0 adds the weight itself (or 1.0), the unweighted branch has no multiply by w.
+template <int ND, int S, bool W, int N>
+__device__ __forceinline__ double stencil_value(const double (&wx)[N], const double (&wy)[N], const double (&wz)[N],
+                                                int a, int c, int d, double w) {
+    if (S == 0) return W ? w : 1.0;
+    if (ND == 1) return W ? __dmul_rn(wx[a], w) : wx[a];
+    double v = __dmul_rn(wx[a], wy[c]);
+    if (ND == 3) v = __dmul_rn(v, wz[d]);
+    return W ? __dmul_rn(v, w) : v;
+}
+
 // Streaming 8-byte load: read-only path, do not allocate in L1 and mark the line evict-first
 // in L2 (each particle is touched exactly once; the L2 belongs to the grid the reductions
 // hit).  ptxas folds the policy into the load's descriptor, it costs no instruction.
