@@ -28,56 +28,20 @@ constexpr int kUnroll = 4;      // independent particle loads in flight per thre
 template <int ND, int S, bool W>
 __device__ __forceinline__ void deposit_particle_global(const DepositParams &P, double x, double y,
                                                         double z, double w) {
-    if (S == 0) {
-        int cx = 0, cy = 0, cz = 0;
-        bool ok = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], cx);
-        if (ND >= 2) ok = ngp_axis(y, P.lo[1], P.inv[1], P.fbins[1], cy) && ok;
-        if (ND >= 3) ok = ngp_axis(z, P.lo[2], P.inv[2], P.fbins[2], cz) && ok;
-        if (!ok || cx < P.slab_lo || cx >= P.slab_hi) return;
-        int64_t lin = cx;
-        if (ND >= 2) lin = lin * P.dims[1] + cy;
-        if (ND >= 3) lin = lin * P.dims[2] + cz;
-        red_add(P.grid + lin, W ? w : 1.0);
-        return;
-    }
-    constexpr int SS = S == 0 ? 1 : S;   // keeps the templates below well-formed for S == 0
-    constexpr int NW = SS + 1;
+    constexpr int NW = StencilWidth<S>::value;
+    constexpr int NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
+    int b[3];
     double wx[NW], wy[NW], wz[NW];
-    int bx = 0, by = 0, bz = 0;
-    bool ok = shape_axis<SS, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], bx, wx);
-    if (ND >= 2) ok = shape_axis<SS, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], by, wy) && ok;
-    if (ND >= 3) ok = shape_axis<SS, (SS == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], bz, wz) && ok;
-    if (!ok || bx < P.slab_lo || bx >= P.slab_hi) return;
-    if (ND == 1) {
-        double *g = P.grid + bx;
+    if (!particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) || b[0] < P.slab_lo || b[0] >= P.slab_hi) return;
+    const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
+    double *g = P.grid + ((int64_t)b[0] * g1 + b[1]) * g2 + b[2];
 #pragma unroll
-        for (int i = 0; i < NW; ++i) red_add(g + i, W ? __dmul_rn(wx[i], w) : wx[i]);
-    } else if (ND == 2) {
-        double *g = P.grid + (int64_t)bx * P.dims[1] + by;
+    for (int a = 0; a < NW; ++a)
 #pragma unroll
-        for (int i = 0; i < NW; ++i) {
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
-            for (int j = 0; j < NW; ++j) {
-                const double c = __dmul_rn(wx[i], wy[j]);
-                red_add(g + j, W ? __dmul_rn(c, w) : c);
-            }
-            g += P.dims[1];
-        }
-    } else {
-        const int64_t sy = P.dims[2], sx = (int64_t)P.dims[1] * P.dims[2];
-        double *g = P.grid + bx * sx + by * sy + bz;
-#pragma unroll
-        for (int i = 0; i < NW; ++i)
-#pragma unroll
-            for (int j = 0; j < NW; ++j) {
-                const double cxy = __dmul_rn(wx[i], wy[j]);
-#pragma unroll
-                for (int k = 0; k < NW; ++k) {
-                    const double c = __dmul_rn(cxy, wz[k]);
-                    red_add(g + i * sx + j * sy + k, W ? __dmul_rn(c, w) : c);
-                }
-            }
-    }
+            for (int d = 0; d < NDD; ++d)
+                red_add(g + (a * g1 + c) * g2 + d, stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w));
 }
 
 template <int ND, int S, bool W, bool F>
@@ -164,10 +128,9 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
             const double y = ND >= 2 ? ld_stream(py + i * sy) : 0.0;
             const double z = ND >= 3 ? ld_stream(pz + i * sz) : 0.0;
             if (W) w = particle_weight<F>(P, i);
-            ok = shape_axis<S, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], bx, wx);
-            if (ND >= 2) ok = shape_axis<S, true>(y, P.lo[1], P.inv[1], P.fbins_p1[1], by, wy) && ok;
-            if (ND >= 3) ok = shape_axis<S, (S == 1)>(z, P.lo[2], P.inv[2], P.fbins_p1[2], bz, wz) && ok;
-            ok = ok && bx >= P.slab_lo && bx < P.slab_hi;
+            int b[3];
+            ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) && b[0] >= P.slab_lo && b[0] < P.slab_hi;
+            bx = b[0]; by = b[1]; bz = b[2];
         }
         int lin0 = -1;                                    // padded linear index of the first cell
         if (ok) {
