@@ -585,7 +585,7 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
 }
 
 int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2, int device) {
-    if (n < 0 || !out2 || (n > 0 && !x) || stride < 1) return fail(PTG_EINVAL, "ptg_minmax_host_f64: bad arguments");
+    if (n < 0 || !out2 || (n > 0 && !x)) return fail(PTG_EINVAL, "ptg_minmax_host_f64: bad arguments");
     DeviceGuard guard;
     int rc = guard.enter(device);
     if (rc) return rc;
@@ -593,34 +593,49 @@ int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2
     if ((rc = current_device_state(&d))) return rc;
     std::lock_guard<std::mutex> lk(g_mu);
     if ((rc = ensure_staging(d, 1))) return rc;
-    // chunked: reduce each chunk on the device, combine the (few) partial results on the host
+    // page-locked unit-stride memory is DMA'd in place, anything else goes through the pinned ring
+    const bool direct = stride == 1 && n > 0 && is_pinned(x);
+    if (!direct && (rc = ensure_pinned(d))) return rc;
+    // one array only: a chunk may fill a whole staging slot (4 x the per-array share of a deposit chunk)
+    const int64_t chunk = direct ? 4 * kChunk : 4 * kStageChunk;
+    const int64_t nchunks = n > 0 ? (n + chunk - 1) / chunk : 0;
+    if (nchunks == 0) { out2[0] = NAN; out2[1] = NAN; return PTG_OK; }
+    // every chunk is reduced on the device into its own (min, max) pair; the pairs come home in ONE copy
+    double *partials = nullptr;
+    PTG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&partials), (size_t)nchunks * 16, d->stream[0]));
+    PTG_CUDA(cudaStreamSynchronize(d->stream[0]));         // the other ring streams may use it right away
+    bool slot_used[kSlots] = {};
+    int slot = 0;
+    int64_t c = 0;
+    for (int64_t off = 0; off < n; off += chunk, slot = (slot + 1) % kSlots, ++c) {
+        const int64_t m = n - off < chunk ? n - off : chunk;
+        cudaStream_t st = d->stream[slot];
+        if (direct) {
+            PTG_CUDA(h2d_strided(d->slot[slot], x + off, 1, m, st));
+        } else {
+            if (slot_used[slot]) PTG_CUDA(cudaEventSynchronize(d->h2d_done[slot]));   // pinned slot drained
+            double *pdst[4] = {d->pinned[slot], nullptr, nullptr, nullptr};
+            const double *psrc[4] = {x + off * stride, nullptr, nullptr, nullptr};
+            const int64_t pstr[4] = {stride, 1, 1, 1};
+            gather_to_pinned(pdst, psrc, pstr, m);
+            PTG_CUDA(cudaMemcpyAsync(d->slot[slot], pdst[0], (size_t)m * 8, cudaMemcpyHostToDevice, st));
+            PTG_CUDA(cudaEventRecord(d->h2d_done[slot], st));
+            slot_used[slot] = true;
+        }
+        PTG_CUDA(ptg::minmax_f64(m, d->slot[slot], 1, partials + 2 * c, d->sm_count, st));
+    }
+    for (int k = 0; k < kSlots; ++k) PTG_CUDA(cudaStreamSynchronize(d->stream[k]));
+    std::vector<double> host((size_t)nchunks * 2);
+    PTG_CUDA(cudaMemcpy(host.data(), partials, (size_t)nchunks * 16, cudaMemcpyDeviceToHost));
+    PTG_CUDA(cudaFreeAsync(partials, d->stream[0]));
     double lo = INFINITY, hi = -INFINITY;
     bool nan = false;
-    int slot = 0;
-    double part[kSlots][2] = {};
-    int64_t pending[kSlots];
-    for (int k = 0; k < kSlots; ++k) pending[k] = 0;
-    auto drain = [&](int k) -> int {
-        if (!pending[k]) return PTG_OK;
-        PTG_CUDA(cudaStreamSynchronize(d->stream[k]));
-        if (part[k][0] != part[k][0] || part[k][1] != part[k][1]) nan = true;
-        lo = part[k][0] < lo ? part[k][0] : lo;
-        hi = part[k][1] > hi ? part[k][1] : hi;
-        pending[k] = 0;
-        return PTG_OK;
-    };
-    for (int64_t off = 0; off < n; off += kChunk, slot = (slot + 1) % kSlots) {
-        if ((rc = drain(slot))) return rc;
-        const int64_t m = n - off < kChunk ? n - off : kChunk;
-        cudaStream_t st = d->stream[slot];
-        PTG_CUDA(h2d_strided(d->slot[slot], x + off * stride, stride, m, st));
-        double *res = d->slot[slot] + kChunk;      // second quarter of the slot is free here
-        PTG_CUDA(ptg::minmax_f64(m, d->slot[slot], 1, res, d->sm_count, st));
-        PTG_CUDA(cudaMemcpyAsync(part[slot], res, 16, cudaMemcpyDeviceToHost, st));
-        pending[slot] = m;
+    for (int64_t k = 0; k < nchunks; ++k) {
+        const double a = host[2 * k], b = host[2 * k + 1];
+        if (a != a || b != b) nan = true;
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
     }
-    for (int k = 0; k < kSlots; ++k)
-        if ((rc = drain(k))) return rc;
     out2[0] = nan ? NAN : lo;
     out2[1] = nan ? NAN : hi;
     return PTG_OK;

@@ -41,10 +41,27 @@ def _split_columns(data):
     return data
 
 
-def _extreme(arr, which):
-    if _device.is_cuda_tensor(arr):
-        return _device.minmax(arr)[which]
-    return (np.min, np.max)[which](arr)
+def _minmax(arr, cache):
+    """(min, max) of one axis, computed once: on the GPU for CUDA tensors (ptg_minmax_f64) and for large
+    host arrays (ptg_minmax_host_f64: one pipelined pass over PCIe instead of numpy's two single-threaded
+    passes, _routines.py:117-126), with numpy for small host arrays."""
+    key = id(arr)
+    if key not in cache:
+        if _device.is_cuda_tensor(arr):
+            cache[key] = _device.minmax(arr)
+        elif arr.size >= (1 << 20) and arr.strides[0] % 8 == 0:
+            import ctypes
+            from .. import _lib
+            out = np.empty(2)
+            _lib.check(_lib.load().ptg_minmax_host_f64(arr.size, arr.ctypes.data, arr.strides[0] // 8,
+                                                       out.ctypes.data,
+                                                       -1 if ptg.device_index is None else int(ptg.device_index)))
+            cache[key] = (float(out[0]), float(out[1]))
+        else:
+            if arr.size == 0:
+                raise ValueError('zero-size array to reduction operation minimum which has no identity')
+            cache[key] = (np.min(arr), np.max(arr))
+    return cache[key]
 
 
 def histogramdd(data, **kwargs):
@@ -112,6 +129,7 @@ def histogramdd(data, **kwargs):
 
     # complete the ranges: a missing (or None) end is the data's min / max
     ranges = [[None, None] for _ in data]
+    mm_cache = {}
     for ax, d in enumerate(data):
         for i in (0, 1):
             try:
@@ -121,7 +139,7 @@ def histogramdd(data, **kwargs):
                 if not np.isscalar(ranges[ax][i]):
                     raise ValueError('range="{}" not properly formatted.'.format(kwrange))
             except TypeError:
-                ranges[ax][i] = _extreme(d, i)
+                ranges[ax][i] = _minmax(d, mm_cache)[i]
 
     if ndim == 1:
         h, xedges = ptg.histogram(data[0], range=ranges[0], bins=kwbins[0],

@@ -142,6 +142,17 @@ class TestHistogramdd:
         h2, e2 = histogramdd((self.datax, self.datay), bins=(16, 16), range=((None, 0.9), None), shape=2)
         assert e2[0][0] == self.datax.min() and e2[0][-1] == 0.9 and e2[1][-1] == self.datay.max()
 
+    def test_range_from_large_host_arrays_uses_the_device_reduction(self, histogramdd):
+        rng = np.random.default_rng(3)
+        n = (1 << 21) + 12345
+        x, y = rng.normal(0, 1, n), rng.normal(5, 2, n)
+        h, (ex, ey) = histogramdd((x, y[::-1]), bins=(40, 30), shape=1)
+        assert ex[0] == x.min() and ex[-1] == x.max() and ey[0] == y.min() and ey[-1] == y.max()
+        assert abs(h.base.sum() - n) < 1e-6 * n
+        x[77] = np.nan                                       # NaN propagates into the edges, like numpy
+        _, (ex, _) = histogramdd((x, y), bins=(4, 4), shape=0)
+        assert np.isnan(ex).all()
+
     def test_defaults_and_errors(self, histogramdd):
         h, (e,) = histogramdd(self.datax, range=(0, 1))
         assert h.shape == (800,)                          # default bins, default shape 2
