@@ -160,6 +160,10 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n,
                            const double *lo, const double *inv, const int *bins,
                            double *grid, unsigned flags, int device);
 int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2, int device);
+/* dst_device[i] = src[i * stride] for i in [0, n): host array (pageable or pinned, any element stride)
+ * to a contiguous device array through the same threaded pinned staging ring.  Synchronous.  Used when
+ * several passes need the particles (range completion followed by the deposit): one trip over PCIe. */
+int ptg_upload_host_f64(int64_t n, const double *src, int64_t stride, double *dst_device, int device);
 /* release the cached per-device staging buffers and streams of the host entry points */
 int ptg_release(void);
 

@@ -641,6 +641,41 @@ int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2
     return PTG_OK;
 }
 
+int ptg_upload_host_f64(int64_t n, const double *src, int64_t stride, double *dst_device, int device) {
+    if (n < 0 || (n > 0 && (!src || !dst_device))) return fail(PTG_EINVAL, "ptg_upload_host_f64: bad arguments");
+    DeviceGuard guard;
+    int rc = guard.enter(device);
+    if (rc) return rc;
+    DeviceState *d;
+    if ((rc = current_device_state(&d))) return rc;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if ((rc = ensure_staging(d, 1))) return rc;
+    const bool direct = stride == 1 && n > 0 && is_pinned(src);
+    if (direct) {
+        PTG_CUDA(cudaMemcpyAsync(dst_device, src, (size_t)n * 8, cudaMemcpyHostToDevice, d->stream[0]));
+        PTG_CUDA(cudaStreamSynchronize(d->stream[0]));
+        return PTG_OK;
+    }
+    if ((rc = ensure_pinned(d))) return rc;
+    const int64_t chunk = 4 * kStageChunk;                 // a whole pinned slot per chunk
+    bool slot_used[kSlots] = {};
+    int slot = 0;
+    for (int64_t off = 0; off < n; off += chunk, slot = (slot + 1) % kSlots) {
+        const int64_t m = n - off < chunk ? n - off : chunk;
+        cudaStream_t st = d->stream[slot];
+        if (slot_used[slot]) PTG_CUDA(cudaEventSynchronize(d->h2d_done[slot]));
+        double *pdst[4] = {d->pinned[slot], nullptr, nullptr, nullptr};
+        const double *psrc[4] = {src + off * stride, nullptr, nullptr, nullptr};
+        const int64_t pstr[4] = {stride, 1, 1, 1};
+        gather_to_pinned(pdst, psrc, pstr, m);
+        PTG_CUDA(cudaMemcpyAsync(dst_device + off, pdst[0], (size_t)m * 8, cudaMemcpyHostToDevice, st));
+        PTG_CUDA(cudaEventRecord(d->h2d_done[slot], st));
+        slot_used[slot] = true;
+    }
+    for (int k = 0; k < kSlots; ++k) PTG_CUDA(cudaStreamSynchronize(d->stream[k]));
+    return PTG_OK;
+}
+
 int ptg_release(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     int prev = -1;

@@ -172,3 +172,20 @@ def kinetic_weights(kind, px, py, pz, weight=None, mass=None, c=299792458.0, ele
             weight.data_ptr() if weight is not None else None, strides, float(mass if mass is not None else 1.0),
             float(c), float(elementary_charge), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
     return out
+
+
+def upload(arr, device_index=None):
+    """Host float64 array (any stride, pageable or pinned) -> contiguous CUDA tensor through the library's
+    threaded pinned staging ring (about 4x faster than torch's pageable copy)."""
+    torch = _torch()
+    a = np.asarray(arr, dtype=np.float64)
+    if a.ndim != 1:
+        raise ValueError('1-D array expected')
+    if a.size > 1 and a.strides[0] % 8:
+        a = np.ascontiguousarray(a)
+    dev = torch.device('cuda', torch.cuda.current_device() if device_index is None else int(device_index))
+    out = torch.empty(a.size, dtype=torch.float64, device=dev)
+    if a.size:
+        _lib.check(_lib.load().ptg_upload_host_f64(a.size, a.ctypes.data, a.strides[0] // 8 if a.size > 1 else 1,
+                                                   out.data_ptr(), dev.index))
+    return out

@@ -41,6 +41,18 @@ def _split_columns(data):
     return data
 
 
+def _needs_range(kwrange, ndim):
+    """True when at least one range end has to come from the data."""
+    for ax in range(ndim):
+        for i in (0, 1):
+            try:
+                if kwrange[ax][i] is None:
+                    return True
+            except TypeError:
+                return True
+    return False
+
+
 def _minmax(arr, cache):
     """(min, max) of one axis, computed once: on the GPU for CUDA tensors (ptg_minmax_f64) and for large
     host arrays (ptg_minmax_host_f64: one pipelined pass over PCIe instead of numpy's two single-threaded
@@ -126,6 +138,23 @@ def histogramdd(data, **kwargs):
         data = [np.asarray(d, dtype='float64') for d in data]
         if kwweights is not None:
             kwweights = np.asarray(kwweights, dtype='float64')
+
+    # Large host arrays whose range must first be found are needed twice (min/max, then the deposit):
+    # move them to the GPU once -- through the library's threaded pinned staging ring -- when they fit
+    # comfortably, so that PCIe is crossed one time instead of two.
+    if not on_device and _needs_range(kwrange, ndim) and data[0].size >= (1 << 20):
+        try:
+            torch = _device._torch()
+            free, _ = torch.cuda.mem_get_info()
+            need = 8 * data[0].size * (ndim + (kwweights is not None))
+            if torch.cuda.is_available() and need < free // 2:
+                idx = ptg.device_index
+                data = [_device.upload(d, idx) for d in data]
+                if kwweights is not None:
+                    kwweights = _device.upload(kwweights, idx)
+                on_device = True
+        except ImportError:                                 # no torch: keep the two-pass host route
+            pass
 
     # complete the ranges: a missing (or None) end is the data's min / max
     ranges = [[None, None] for _ in data]
