@@ -19,8 +19,14 @@
 
 namespace ptg {
 
-constexpr int kThreads = 256;
-constexpr int kUnroll = 4;      // independent particle loads in flight per thread
+#ifndef PTG_ROWS_THREADS
+#define PTG_ROWS_THREADS 256
+#endif
+#ifndef PTG_GLOBAL_UNROLL
+#define PTG_GLOBAL_UNROLL 4
+#endif
+constexpr int kThreads = PTG_ROWS_THREADS;
+constexpr int kUnroll = PTG_GLOBAL_UNROLL;      // independent particle loads in flight per thread
 
 // ---------------------------------------------------------------------------------
 // one particle -> REDs (method GLOBAL)

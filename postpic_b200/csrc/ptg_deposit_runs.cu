@@ -22,9 +22,15 @@
 
 namespace ptg {
 
-constexpr int kRT = 256;      // threads per CTA
+#ifndef PTG_RUNS_THREADS
+#define PTG_RUNS_THREADS 256
+#endif
+#ifndef PTG_RUNS_BATCHES
+#define PTG_RUNS_BATCHES 2
+#endif
+constexpr int kRT = PTG_RUNS_THREADS;      // threads per CTA
 constexpr int kRK = 4;        // consecutive particles per load batch
-constexpr int kRB = 2;        // batches per thread between two warp-level merges (8 consecutive particles;
+constexpr int kRB = PTG_RUNS_BATCHES;        // batches per thread between two warp-level merges (8 consecutive particles;
                               // 16 measured slower: a lane's 128-byte span is then fetched in four visits)
 
 // 256-bit load (sm_100: LDG.E.NA.EFL2.256): the four consecutive doubles of one lane are exactly one
