@@ -145,9 +145,9 @@ def histogramdd(data, **kwargs):
     if not on_device and _needs_range(kwrange, ndim) and data[0].size >= (1 << 20):
         try:
             torch = _device._torch()
-            free, _ = torch.cuda.mem_get_info()
+            free = torch.cuda.mem_get_info()[0] if torch.cuda.is_available() else 0
             need = 8 * data[0].size * (ndim + (kwweights is not None))
-            if torch.cuda.is_available() and need < free // 2:
+            if need < free // 2:
                 idx = ptg.device_index
                 data = [_device.upload(d, idx) for d in data]
                 if kwweights is not None:
