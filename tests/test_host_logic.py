@@ -91,6 +91,13 @@ def test_no_cpu_fallback_without_gpu():
         ptg.histogram2d(x, x, range=((0, 1), (0, 1)), bins=(4, 4), shape=0)
     with pytest.raises(_lib.NoDeviceError):
         _lib.device_info()
+    # the front door too, also on the large-array / range-from-data route (device min/max + upload)
+    from postpic_b200 import histogramdd
+    big = np.random.default_rng(0).random(1 << 21)
+    with pytest.raises(_lib.NoDeviceError):
+        histogramdd((big, big), bins=(8, 8))
+    with pytest.raises(_lib.NoDeviceError):
+        histogramdd(x, bins=8, range=(0, 1))
     # argument errors are still reported before any device work
     with pytest.raises(ValueError):
         ptg.histogram2d(x, x[:5], range=((0, 1), (0, 1)), bins=(4, 4))
