@@ -538,3 +538,27 @@ def test_randomised_differential_against_oracle(ptg, oracle):
         checked += 1
     ptg.method = None
     assert checked == 400
+
+
+def test_half_gigabyte_grid_many_slab_passes():
+    """402^3 doubles = 520 MB, four times the L2: eight slab passes for rows / global, cross-checked with
+    the un-slabbed runs kernel; also the largest 2-D grid the 2^31-cell limit admits in one axis."""
+    import torch
+    from postpic_b200 import device
+    n = 5_000_000
+    g = torch.Generator(device='cuda').manual_seed(123)
+    c = [torch.rand(n, dtype=torch.float64, device='cuda', generator=g) for _ in range(3)]
+    w = torch.rand(n, dtype=torch.float64, device='cuda', generator=g)
+    kw = dict(range=[(0, 1)] * 3, bins=(400, 400, 400), shape=1)
+    ref, _ = device.deposit(c, w, method='runs', **kw)
+    for m in ('rows', None):
+        got, _ = device.deposit(c, w, method=m, **kw)
+        assert float((got - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+    del ref, got
+    torch.cuda.empty_cache()
+    # a long, thin 2-D grid: 40000 x 5000 bins = 2e8 cells (1.6 GB)
+    kw = dict(range=[(0, 1), (0, 1)], bins=(40000, 5000), shape=2)
+    a, _ = device.deposit(c[:2], w, method='runs', **kw)
+    b, _ = device.deposit(c[:2], w, method=None, **kw)
+    assert float((a - b).abs().max()) <= 1e-12 * float(a.abs().max())
+    assert abs(float(b.sum()) - float(w.sum())) <= 1e-12 * float(w.sum())
