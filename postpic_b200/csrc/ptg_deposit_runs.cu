@@ -22,6 +22,9 @@
 
 namespace ptg {
 
+#ifndef PTG_RUNS_MERGE_MAX_HEADS
+#define PTG_RUNS_MERGE_MAX_HEADS 20      // warp merge only when the 32 lanes hold at most this many runs
+#endif
 #ifndef PTG_RUNS_THREADS
 #define PTG_RUNS_THREADS 256
 #endif
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
         const bool head = lane == 0 || prev != key;
         const unsigned heads = __ballot_sync(0xffffffffu, head);
         bool mine = cur >= 0;
-        if (__popc(heads) <= 20) {
+        if (__popc(heads) <= PTG_RUNS_MERGE_MAX_HEADS) {
             const unsigned above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
             const int next_head = above ? __ffs(above) - 1 : 32;
 #pragma unroll
