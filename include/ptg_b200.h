@@ -143,6 +143,33 @@ int ptg_deposit_fused_f64(int ndim, int shape, int64_t n,
                           const int64_t *pstrides, double mass, double c, double elementary_charge,
                           void *stream);
 
+/* ---- the general device entry: everything above plus a selection mask, in one argument block ----- */
+/* mask (device pointer, one byte per particle, stride in bytes; NULL = all): only particles with a
+ * non-zero mask byte are deposited -- MultiSpecies.filter / compress (particles.py:219-232, :561-582) as
+ * predicated deposition, no compressed copies of the particle arrays.  Set struct_size =
+ * sizeof(ptg_deposit_args); unused members zero / NULL.                                           */
+typedef struct ptg_deposit_args {
+    size_t struct_size;
+    int ndim, shape;
+    int64_t n;
+    const double *x, *y, *z, *w;
+    const int64_t *strides;             /* [4] or NULL */
+    const double *lo, *inv;
+    const int *bins;
+    double *grid;
+    unsigned flags;
+    const unsigned char *mask;
+    int64_t mask_stride;
+    int fuse_kind;                      /* 0 = no fused weight expression, else PTG_W_* */
+    const double *px, *py, *pz;
+    const int64_t *pstrides;            /* [3] or NULL */
+    double mass, c, elementary_charge;
+    void *workspace;
+    size_t workspace_bytes;
+    void *stream;
+} ptg_deposit_args;
+int ptg_deposit_ex_f64(const ptg_deposit_args *args);
+
 /* ---- host-buffer drop-in: H2D + deposit + D2H in one call --------------------------- */
 /*
  * Same meaning as ptg_deposit_f64 but x,y,z,w and grid are HOST pointers.  Particles

@@ -43,6 +43,16 @@ _c = ctypes
 _P = _c.c_void_p
 _I64 = _c.c_int64
 
+class DepositArgs(_c.Structure):
+    """ptg_deposit_args of include/ptg_b200.h (argument block of ptg_deposit_ex_f64)."""
+    _fields_ = [("struct_size", _c.c_size_t), ("ndim", _c.c_int), ("shape", _c.c_int), ("n", _I64),
+                ("x", _P), ("y", _P), ("z", _P), ("w", _P), ("strides", _P), ("lo", _P), ("inv", _P),
+                ("bins", _P), ("grid", _P), ("flags", _c.c_uint), ("mask", _P), ("mask_stride", _I64),
+                ("fuse_kind", _c.c_int), ("px", _P), ("py", _P), ("pz", _P), ("pstrides", _P),
+                ("mass", _c.c_double), ("c", _c.c_double), ("elementary_charge", _c.c_double),
+                ("workspace", _P), ("workspace_bytes", _c.c_size_t), ("stream", _P)]
+
+
 # name -> (restype, argtypes); every symbol include/ptg_b200.h declares
 SIGNATURES = {
     "ptg_abi_version": (_c.c_int, []),
@@ -54,6 +64,7 @@ SIGNATURES = {
                                    _c.c_uint, _P, _c.c_size_t, _P]),
     "ptg_deposit_fused_f64": (_c.c_int, [_c.c_int, _c.c_int, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _c.c_uint,
                                          _c.c_int, _P, _P, _P, _P, _c.c_double, _c.c_double, _c.c_double, _P]),
+    "ptg_deposit_ex_f64": (_c.c_int, [_P]),
     "ptg_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _I64, _P, _c.c_uint]),
     "ptg_padded_cells": (_I64, [_c.c_int, _c.c_int, _P]),
     "ptg_minmax_f64": (_c.c_int, [_I64, _P, _I64, _P, _P]),

@@ -152,6 +152,11 @@ struct FuseSpec {
     double mass, c, qe;
 };
 
+struct MaskSpec {
+    const unsigned char *mask;
+    int64_t stride;
+};
+
 // Probe verdicts live in a ring: an AUTO/TILED call takes the next entry and its kernels read it in
 // stream order.  4096 entries = the number of such calls that may be in flight per device at once
 // (the host pipeline below never has more than 8).
@@ -176,9 +181,14 @@ int next_tile_config(DeviceState *d, ptg::TileConfig **out) {
 int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double *x, const double *y,
                    const double *z, const double *w, const int64_t *strides, const double *lo,
                    const double *inv, const int *bins, double *grid, unsigned flags, cudaStream_t st,
-                   void *workspace = nullptr, size_t workspace_bytes = 0, const FuseSpec *fuse = nullptr) {
+                   void *workspace = nullptr, size_t workspace_bytes = 0, const FuseSpec *fuse = nullptr,
+                   const MaskSpec *mask = nullptr) {
     ptg::DepositParams P;
     fill_params(P, ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid);
+    if (mask && mask->mask) {
+        P.mask = mask->mask;
+        P.mstride = mask->stride;
+    }
     if (fuse) {
         P.fuse_kind = fuse->kind;
         for (int k = 0; k < 3; ++k) { P.q[k] = fuse->q[k]; P.qstride[k] = fuse->qstride[k]; }
@@ -449,6 +459,29 @@ int ptg_deposit_fused_f64(int ndim, int shape, int64_t n, const double *x, const
     f.mass = mass; f.c = c; f.qe = elementary_charge;
     return deposit_device(d, ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid, flags, (cudaStream_t)stream,
                           nullptr, 0, &f);
+}
+
+int ptg_deposit_ex_f64(const ptg_deposit_args *a) {
+    if (!a || a->struct_size < sizeof(ptg_deposit_args)) return fail(PTG_EINVAL, "ptg_deposit_ex_f64: bad argument block");
+    int rc = validate(a->ndim, a->shape, a->n, a->x, a->y, a->z, a->lo, a->inv, a->bins, a->grid);
+    if (rc) return rc;
+    DeviceState *d;
+    if ((rc = current_device_state(&d))) return rc;
+    FuseSpec f;
+    const FuseSpec *fp = nullptr;
+    if (a->fuse_kind != 0) {
+        if (a->fuse_kind < PTG_W_GAMMA_M1 || a->fuse_kind > PTG_W_P)
+            return fail(PTG_EINVAL, "unknown weight expression kind %d", a->fuse_kind);
+        if (a->n > 0 && (!a->px || !a->py || !a->pz)) return fail(PTG_EINVAL, "momentum pointer is NULL");
+        f.kind = a->fuse_kind;
+        f.q[0] = a->px; f.q[1] = a->py; f.q[2] = a->pz;
+        for (int k = 0; k < 3; ++k) f.qstride[k] = a->pstrides ? a->pstrides[k] : 1;
+        f.mass = a->mass; f.c = a->c; f.qe = a->elementary_charge;
+        fp = &f;
+    }
+    MaskSpec m{a->mask, a->mask_stride ? a->mask_stride : 1};
+    return deposit_device(d, a->ndim, a->shape, a->n, a->x, a->y, a->z, a->w, a->strides, a->lo, a->inv, a->bins,
+                          a->grid, a->flags, (cudaStream_t)a->stream, a->workspace, a->workspace_bytes, fp, &m);
 }
 
 int ptg_minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, void *stream) {

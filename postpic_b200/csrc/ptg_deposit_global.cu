@@ -69,14 +69,15 @@ __global__ void __launch_bounds__(kThreads) k_deposit_global(const DepositParams
             w[u] = W ? particle_weight<F>(P, k) : 1.0;
         }
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) deposit_particle_global<ND, S, W>(P, x[u], y[u], z[u], w[u]);
+        for (int u = 0; u < kUnroll; ++u)
+            if (particle_selected(P, i + u * nthreads)) deposit_particle_global<ND, S, W>(P, x[u], y[u], z[u], w[u]);
     }
     for (; i < P.n; i += nthreads) {
         const double x = ld_stream(px + i * sx);
         const double y = ND >= 2 ? ld_stream(py + i * sy) : 0.0;
         const double z = ND >= 3 ? ld_stream(pz + i * sz) : 0.0;
         const double w = W ? particle_weight<F>(P, i) : 1.0;
-        deposit_particle_global<ND, S, W>(P, x, y, z, w);
+        if (particle_selected(P, i)) deposit_particle_global<ND, S, W>(P, x, y, z, w);
     }
 }
 
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
         double wx[NW], wy[NW], wz[NW];
         int bx = 0, by = 0, bz = 0;
         double w = 1.0;
-        bool ok = i < end;
+        bool ok = i < end && particle_selected(P, i);
         if (ok) {
             const double x = ld_stream(px + i * sx);
             const double y = ND >= 2 ? ld_stream(py + i * sy) : 0.0;

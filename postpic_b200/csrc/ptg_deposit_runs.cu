@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
             for (int j = 0; j < kRK; ++j) {
                 int b[3];
                 double wx[NW], wy[NW], wz[NW];
-                const bool ok = particle_stencil<ND, S>(P, x[j], y[j], z[j], b, wx, wy, wz) && j < valid;
+                const bool ok = particle_stencil<ND, S>(P, x[j], y[j], z[j], b, wx, wy, wz) && j < valid &&
+                                particle_selected(P, i0 + j);
                 if (!ok) continue;
                 const double wj = W ? w[j] : 1.0;
                 if (WD && W && !(fabs(wj) <= 1.79769313486231570e308)) {

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_cell_keys(const DepositParams P, uint32
         const double z = ND >= 3 ? ld_stream(P.p[2] + i * P.stride[2]) : 0.0;
         int b[3];
         double wx[StencilWidth<S>::value], wy[StencilWidth<S>::value], wz[StencilWidth<S>::value];
-        const bool ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz);
+        const bool ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) && particle_selected(P, i);
         uint32_t key = cells;
         if (ok) key = (uint32_t)((b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2]);    // dims beyond ndim are 1
         keys[i] = key;

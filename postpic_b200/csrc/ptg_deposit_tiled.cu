@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
         // ---- stencil in registers --------------------------------------------------
         int b[3];
         double wx[NW], wy[NW], wz[NW];
-        const bool ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) && i < end;
+        const bool ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) && i < end && particle_selected(P, i);
         // value of stencil cell (a, c, d), reference operation order: ((wx*wy)*wz)*w
         auto value = [&](int a, int c, int d) -> double { return stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w); };
         constexpr int NV = ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW;
@@ -465,10 +465,11 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
             w[u] = W ? particle_weight<F>(P, k) : 1.0;
         }
 #pragma unroll
-        for (int u = 0; u < kSU; ++u) one(x[u], y[u], z[u], w[u]);
+        for (int u = 0; u < kSU; ++u)
+            if (particle_selected(P, i + u * nthreads)) one(x[u], y[u], z[u], w[u]);
     }
     for (; i < P.n; i += nthreads)
-        one(ld_stream(px + i * sx), ND >= 2 ? ld_stream(py + i * sy) : 0.0, ND >= 3 ? ld_stream(pz + i * sz) : 0.0,
+        if (particle_selected(P, i)) one(ld_stream(px + i * sx), ND >= 2 ? ld_stream(py + i * sy) : 0.0, ND >= 3 ? ld_stream(pz + i * sz) : 0.0,
             W ? particle_weight<F>(P, i) : 1.0);
     __syncthreads();
     for (int c = threadIdx.x; c < cells; c += kST) {

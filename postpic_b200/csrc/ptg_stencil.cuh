@@ -118,11 +118,19 @@ struct DepositParams {
     int64_t stag_copy;      // distance between the two copies, in doubles
     // fused kinetic weight (0 = off): the particle's weight is weight[i] (or 1) times a scalar of
     // its momentum, evaluated in the kernel instead of in a separate pass
+    // predicated deposition (null = every particle): particle i takes part iff mask[i * mstride] != 0 --
+    // postpic's filter / compress (particles.py:219-232, :561-582) without materialising compressed copies
+    const unsigned char *mask;
+    int64_t mstride;
     int fuse_kind;
     const double *q[3];     // px, py, pz
     int64_t qstride[3];
     double f_mass, f_mc2, f_c2, f_qe;   // mass, (mass*c)^2, c^2, elementary charge
 };
+
+__device__ __forceinline__ bool particle_selected(const DepositParams &P, int64_t i) {
+    return P.mask == nullptr || P.mask[i * P.mstride] != 0;
+}
 
 // Stencil of one particle on all axes: accept test, padded base cell b[a] and the per-axis weights
 // (a single 1.0 for shape 0).  Axis kinds as in the reference: x on the truncated int, y on the raw

@@ -63,13 +63,15 @@ class Plan(object):
         return float(np.prod([e[1] - e[0] for e in self.edges]))
 
 
-def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, stream=None, fused=None):
+def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, stream=None, fused=None, mask=None):
     """Deposit CUDA tensors `coords` (+ optional `weights`) into the padded CUDA tensor `grid`.
 
     Asynchronous on `stream` (default: torch's current stream on grid.device).
     `fused` = dict(kind=, px=, py=, pz=, mass=[, c=, elementary_charge=]) multiplies every particle's
     weight by a kinetic scalar of its momentum inside the deposit kernel (ptg_deposit_fused_f64):
-    `weights='Ekin_MeV'` of createField without materialising a weights array."""
+    `weights='Ekin_MeV'` of createField without materialising a weights array.
+    `mask` = bool / uint8 CUDA tensor: only particles with a non-zero entry are deposited
+    (MultiSpecies.filter as predicated deposition, no compressed copies)."""
     torch = _torch()
     lib = _lib.load()
     if len(coords) != plan.ndim:
@@ -93,6 +95,36 @@ def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, strea
     strides.append(weights.stride(0) if (weights is not None and n > 1) else 1)
     cstr = (ctypes.c_int64 * 4)(*strides)
     flags = _lib.METHODS[method] | (_lib.ZERO_GRID if zero else 0)
+    if mask is not None:
+        if mask.dtype not in (torch.bool, torch.uint8) or mask.dim() != 1 or mask.numel() < n or \
+                mask.device != grid.device:
+            raise ValueError('mask must be a 1-D bool / uint8 CUDA tensor with one entry per particle')
+        args = _lib.DepositArgs()
+        args.struct_size = ctypes.sizeof(_lib.DepositArgs)
+        args.ndim, args.shape, args.n = plan.ndim, plan.shape, n
+        args.x, args.y, args.z, args.w = ptr[0], ptr[1], ptr[2], ptr[3]
+        args.strides = ctypes.cast(cstr, ctypes.c_void_p)
+        args.lo, args.inv = plan.lo.ctypes.data, plan.inv.ctypes.data
+        args.bins = ctypes.cast(plan.cbins, ctypes.c_void_p)
+        args.grid, args.flags = grid.data_ptr(), flags
+        args.mask, args.mask_stride = (mask.data_ptr() if n else None), (mask.stride(0) if n > 1 else 1)
+        keep = []
+        if fused is not None:
+            q = [fused['px'], fused['py'], fused['pz']]
+            for t, nm in zip(q, ('px', 'py', 'pz')):
+                _check_tensor(t, nm)
+            qstr = (ctypes.c_int64 * 3)(*[t.stride(0) if n > 1 else 1 for t in q])
+            keep.append(qstr)
+            args.fuse_kind = WEIGHT_KINDS[fused['kind']]
+            args.px, args.py, args.pz = (t.data_ptr() if n else None for t in q)
+            args.pstrides = ctypes.cast(qstr, ctypes.c_void_p)
+            args.mass = float(fused['mass'])
+            args.c = float(fused.get('c', 299792458.0))
+            args.elementary_charge = float(fused.get('elementary_charge', 1.602176634e-19))
+        with torch.cuda.device(grid.device):
+            args.stream = torch.cuda.current_stream().cuda_stream if stream is None else stream
+            _lib.check(lib.ptg_deposit_ex_f64(ctypes.byref(args)))
+        return grid
     with torch.cuda.device(grid.device):
         st = torch.cuda.current_stream().cuda_stream if stream is None else stream
         if fused is None:
@@ -115,7 +147,7 @@ def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, strea
     return grid
 
 
-def deposit(coords, weights=None, range=None, bins=None, shape=0, method=None, fused=None):
+def deposit(coords, weights=None, range=None, bins=None, shape=0, method=None, fused=None, mask=None):
     """-> (padded grid CUDA tensor, plan).  `plan.interior` slices out the histogram."""
     torch = _torch()
     coords = list(coords)
@@ -124,7 +156,7 @@ def deposit(coords, weights=None, range=None, bins=None, shape=0, method=None, f
         range = [range]
     plan = Plan(range, as_bins(bins[0] if (nd == 1 and np.ndim(bins)) else bins, nd), shape)
     grid = torch.empty(plan.dims, dtype=torch.float64, device=coords[0].device)
-    deposit_into(grid, plan, coords, weights, method=method, zero=True, fused=fused)
+    deposit_into(grid, plan, coords, weights, method=method, zero=True, fused=fused, mask=mask)
     return grid, plan
 
 

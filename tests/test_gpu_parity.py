@@ -562,3 +562,36 @@ def test_half_gigabyte_grid_many_slab_passes():
     b, _ = device.deposit(c[:2], w, method=None, **kw)
     assert float((a - b).abs().max()) <= 1e-12 * float(a.abs().max())
     assert abs(float(b.sum()) - float(w.sum())) <= 1e-12 * float(w.sum())
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_masked_deposit_equals_compressed_copy(method):
+    """ptg_deposit_ex_f64 with a selection mask == depositing the compressed arrays (what postpic's
+    filter/compress materialises), for every method, random and cell-ordered input, bool and strided masks."""
+    import torch
+    from postpic_b200 import device
+    n = 3_000_000
+    g = torch.Generator(device='cuda').manual_seed(31)
+    x = torch.rand(n, dtype=torch.float64, device='cuda', generator=g) * 1.04 - 0.02
+    y = torch.rand(n, dtype=torch.float64, device='cuda', generator=g) * 1.04 - 0.02
+    w = torch.rand(n, dtype=torch.float64, device='cuda', generator=g)
+    m = torch.rand(n, device='cuda', generator=g) < 0.37
+    order = torch.argsort((x.clamp(0, 1) * 150).floor() * 150 + (y.clamp(0, 1) * 150).floor())
+    for idx in (None, order):
+        sel = (lambda t: t) if idx is None else (lambda t: t[idx].contiguous())
+        xs, ys, ws, ms = sel(x), sel(y), sel(w), sel(m)
+        for shape in ((0, 1, 2) if method != 'runs_wide' else (0, 1)):
+            kw = dict(range=[(0, 1), (0, 1)], bins=(150, 150), shape=shape)
+            ref, _ = device.deposit([xs[ms], ys[ms]], ws[ms], method='global', **kw)
+            got, _ = device.deposit([xs, ys], ws, method=method, mask=ms, **kw)
+            assert float((got - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+            got, _ = device.deposit([xs, ys], None, method=method, mask=ms.to(torch.uint8), **kw)
+            ref, _ = device.deposit([xs[ms], ys[ms]], None, method='global', **kw)
+            assert float((got - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+    # all-false and all-true masks
+    kw = dict(range=[(0, 1), (0, 1)], bins=(64, 64), shape=2)
+    got, _ = device.deposit([x, y], w, method=method, mask=torch.zeros(n, dtype=torch.bool, device='cuda'), **kw)
+    assert not got.any()
+    got, _ = device.deposit([x, y], w, method=method, mask=torch.ones(n, dtype=torch.bool, device='cuda'), **kw)
+    ref, _ = device.deposit([x, y], w, method='global', **kw)
+    assert float((got - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
