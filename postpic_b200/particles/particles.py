@@ -202,11 +202,34 @@ class MultiSpecies(object):
 
     def __init__(self, *sources):
         self._sources = list(sources)
+        self._filters = []          # scalar conditions set by filter(); evaluated per species on demand
+
+    def filter(self, condition):
+        """A new MultiSpecies restricted to the particles for which `condition` (an expression of the
+        per-particle scalars, e.g. 'gamma > 2') is true (particles.py:561-582).  Host species are
+        compressed like in the reference; device-resident species keep their arrays and carry the
+        condition as a selection mask that the deposit kernels apply (predicated deposition)."""
+        out = MultiSpecies(*self._sources)
+        out._filters = self._filters + [condition]
+        return out
+
+    def _mask_of(self, source):
+        """Boolean selection of one species under all filters, or None."""
+        if not self._filters:
+            return None
+        single = MultiSpecies(source)
+        mask = None
+        for cond in self._filters:
+            m = single(cond)
+            mask = m if mask is None else (mask & m)
+        return mask
 
     # -- the small part of the container API the dispatch below relies on ----------
     @property
     def npart(self):
-        return sum(len(s) for s in self._sources)
+        if not self._filters:
+            return sum(len(s) for s in self._sources)
+        return int(sum(int(self._mask_of(s).sum()) for s in self._sources))
 
     @property
     def nspecies(self):
@@ -221,6 +244,8 @@ class MultiSpecies(object):
         return self.npart
 
     def __add__(self, other):
+        if self._filters or other._filters:
+            raise NotImplementedError('adding filtered collections is not supported by this shim')
         return MultiSpecies(*(self._sources + other._sources))
 
     def getcompresslog(self):
@@ -254,6 +279,8 @@ class MultiSpecies(object):
                 raise KeyError(str(exc))
             if np.ndim(val) == 0 and not _device.is_cuda_tensor(val):
                 val = s.atomic('weight') * 0 + float(val) if 'weight' in s._arrays else np.full(len(s), float(val))
+            if self._filters and not getattr(self, '_raw', False):
+                val = val[self._mask_of(s)]          # compressed view of the species (reference behaviour)
             parts.append(val)
         if not parts:
             return np.empty(0, dtype=np.float64)
@@ -317,8 +344,14 @@ class MultiSpecies(object):
 
         if simgrid:
             simextent = True
+        on_device = bool(self._sources) and all(s.device is not None for s in self._sources)
         try:
-            data = [self(sp) for sp in sps]
+            if on_device and self.npart > 0:
+                data = None                       # evaluated per species below, nothing is concatenated
+                for sp in sps:                    # (unknown scalars must still raise here)
+                    MultiSpecies(self._sources[0])(sp)
+            else:
+                data = [self(sp) for sp in sps]
         except KeyError:
             if not force:
                 raise
@@ -332,7 +365,7 @@ class MultiSpecies(object):
                 tmp = self.simgridpoints(getattr(sp, 'symbol', sp))
                 if tmp is not None:
                     bins[i] = tmp
-        if len(data[0]) == 0:                       # no particles: an all-zero histogram
+        if data is not None and len(data[0]) == 0:  # no particles: an all-zero histogram
             h = np.zeros(bins)
 
             def edges_of(r, nb):
@@ -340,7 +373,7 @@ class MultiSpecies(object):
             edges = [edges_of(r, bins[i]) for i, r in zip(range(h.ndim), ranges)]
             return h, edges
 
-        if all(s.device is not None for s in self._sources):
+        if data is None:
             return self._createHistgram_per_species(sps, ranges, weights, bins, shape)
         w = self._weights(weights)
         h, edges = histogramdd(data, weights=w, range=ranges, bins=bins, shape=shape)
@@ -358,6 +391,7 @@ class MultiSpecies(object):
         torch = _device._torch()
         nd = len(sps)
         singles = [MultiSpecies(s) for s in self._sources if len(s) > 0]
+        masks = [self._mask_of(m._sources[0]) for m in singles]
         dev = self._sources[0].device
         c = _sc.c if _sc is not None else _CONSTANTS['c']
         qe = _sc.elementary_charge if _sc is not None else _CONSTANTS['elementary_charge']
@@ -382,12 +416,13 @@ class MultiSpecies(object):
             else:
                 w, fused = m._weights(weights), None
             per.append((d, w, fused))
+        per = [p + (mk,) for p, mk in zip(per, masks)]
         rng = []
         for a in range(nd):
             r = ranges[a]
             lo, hi = (None, None) if r is None else (r[0], r[1])
             if lo is None or hi is None:
-                mm = [_device.minmax(d[a].contiguous() if d[a].stride(0) < 1 else d[a]) for d, _, _ in per]
+                mm = [_device.minmax(d[a] if mk is None else d[a][mk]) for d, _, _, mk in per]
                 lo = min(m[0] for m in mm) if lo is None else lo
                 hi = max(m[1] for m in mm) if hi is None else hi
             rng.append((lo, hi))
@@ -397,10 +432,10 @@ class MultiSpecies(object):
             bins = (bins,) * nd
         plan = _device.Plan(rng, as_bins(bins[0] if nd == 1 else bins, nd), 2 if shape is None else shape)
         grid = torch.zeros(plan.dims, dtype=torch.float64, device=self._sources[0].device)
-        for d, w, fused in per:
+        for d, w, fused, mk in per:
             _device.deposit_into(grid, plan, [t if t.dtype == torch.float64 else t.to(torch.float64) for t in d],
                                  w if (w is None or w.dtype == torch.float64) else w.to(torch.float64), zero=False,
-                                 fused=fused)
+                                 fused=fused, mask=mk)
         _device.scale_(grid, 1.0 / plan.cell_volume())
         h = grid.cpu().numpy()[plan.interior]
         return h, tuple(plan.edges)

@@ -281,6 +281,31 @@ class TestCreateField:
             assert np.allclose(fd.matrix, fh.matrix, rtol=1e-10, atol=1e-12 * np.abs(fh.matrix).max())
             assert fd.matrix.base is not None and fd.infostring == '50000 npart in 2 species'
 
+    def test_filter_is_predicated_deposition_on_device(self):
+        """MultiSpecies.filter: host species are compressed (reference behaviour), device species carry
+        a mask into the kernels; both give the same field, also with fused energy weights."""
+        from postpic_b200 import MultiSpecies, ArraySource
+        import torch
+        a = self._species(40000)
+        host = MultiSpecies(a).filter('gamma > 1.2').filter('x > -1')
+
+        def dev(src):
+            return ArraySource(src.species, {k: (torch.from_numpy(v).cuda() if isinstance(v, np.ndarray) else v)
+                                             for k, v in src._arrays.items()}, extent=src.extent)
+        device_ms = MultiSpecies(dev(a), dev(a)).filter('gamma > 1.2').filter('x > -1')
+        assert 0 < host.npart < 40000 and device_ms.npart == 2 * host.npart
+        for kw in (dict(bins=[48, 40], rangex=(-3, 3), rangey=(-3, 3), shape=2),
+                   dict(bins=[48, 40], shape=1, weights='Ekin_MeV'),                # ranges from the selected particles
+                   dict(bins=[30], shape=3, weights='gamma')):
+            axes = ('x', 'y')[:len(kw['bins'])]
+            fh = host.createField(*axes, **kw)
+            fd = device_ms.createField(*axes, **kw)
+            assert all(np.array_equal(p.grid_node, q.grid_node) for p, q in zip(fh.axes, fd.axes))
+            assert np.allclose(fd.matrix, 2 * fh.matrix, rtol=1e-10, atol=1e-12 * np.abs(fh.matrix).max())
+        none = MultiSpecies(dev(a)).filter('gamma > 1e9')
+        f = none.createField('x', 'y', bins=[4, 4], rangex=(-1, 1), rangey=(-1, 1))
+        assert f.matrix.shape == (4, 4) and not f.matrix.any()
+
     def test_empty_and_aliases(self):
         from postpic_b200 import MultiSpecies, ArraySource
         empty = MultiSpecies(ArraySource('none', dict(x=np.empty(0), y=np.empty(0), weight=np.empty(0))))

@@ -183,6 +183,15 @@ def test_multispecies_dispatch_on_cpu_stack(cpu_stack, monkeypatch, oracle):
     h, e = oracle.histogram(a['x'], weights=ek, range=(-3, 3), bins=32, shape=3)
     assert np.allclose(f3.matrix, h / (e[1] - e[0]), rtol=1e-12)
     assert f3.name == 'Ekin_MeVelectron'
+    # filter(): host species are compressed, like MultiSpecies.filter in the reference (particles.py:561-582)
+    sel = p.filter('x > 0').filter('gamma > 1.1')
+    keep = (a['x'] > 0) & (np2 / (np.sqrt(1 + np2) + 1) + 1 > 1.1)
+    assert sel.npart == int(keep.sum()) and 0 < sel.npart < n
+    f4 = sel.createField('x', 'y', bins=[16, 12], rangex=(-3, 3), rangey=(-3, 3), shape=1)
+    h, ex, ey = oracle.histogram2d(a['x'][keep], a['y'][keep], weights=np.full(int(keep.sum()), 2.0),
+                                   range=((-3, 3), (-3, 3)), bins=(16, 12), shape=1)
+    assert np.allclose(f4.matrix, h / ((ex[1] - ex[0]) * (ey[1] - ey[0])), rtol=1e-14)
+    assert f4.infostring == '%d npart in 1 species' % keep.sum()
     # simgrid is a no-op for bins (the reference's simgridpoints returns None)
     assert p.createField('x', 'y', bins=[7, 9], simgrid=True).matrix.shape == (7, 9)
     with pytest.raises(TypeError):
