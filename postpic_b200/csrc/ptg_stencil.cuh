@@ -129,6 +129,9 @@ struct DepositParams {
 };
 
 __device__ __forceinline__ bool particle_selected(const DepositParams &P, int64_t i) {
+#ifdef PTG_NO_MASK
+    return true;                       // A/B builds only
+#endif
     return P.mask == nullptr || P.mask[i * P.mstride] != 0;
 }
 
