@@ -102,6 +102,40 @@ class ArraySource(object):
     def __len__(self):
         return self._n
 
+    @classmethod
+    def dummy(cls, n, dimensions=2, seed=0, device=None):
+        """The synthetic electron species of postpic's dummy reader (datareader/dummy.py:43-61, :133-176,
+        :177-201), the reference's only particle fixture: np.random.seed(seed); x, y, z ~ N(0,1);
+        px = roll(x,1)**2 * me*c, py = roll(x,2) * me*c, pz = roll(x,3) * me*c; weight 1; shuffled ids;
+        simulation extent x (-2,10), y (-5,5), z (-4,4).  With `device` the arrays go straight into
+        device buffers through the library's pinned staging ring."""
+        me, c, qe = 9.109383e-31, 299792458.0, 1.602176565e-19       # helper.PhysicalConstants
+        state = np.random.get_state()
+        try:
+            if seed is not None:
+                np.random.seed(seed)
+            n = int(n)
+            arrs = {'x': np.random.normal(size=n)}
+            if dimensions > 1:
+                arrs['y'] = np.random.normal(size=n)
+            if dimensions > 2:
+                arrs['z'] = np.random.normal(size=n)
+            x = arrs['x']
+            arrs['px'] = np.roll(x, 1) ** 2 * (me * c)
+            arrs['py'] = np.roll(x, 2) * (me * c)
+            arrs['pz'] = np.roll(x, 3) * (me * c)
+            ids = np.arange(n)
+            np.random.shuffle(ids)
+            arrs['id'] = ids.astype(np.float64)
+        finally:
+            np.random.set_state(state)
+        if device is not None:
+            idx = _device._torch().device(device).index
+            arrs = {k: _device.upload(v, idx) for k, v in arrs.items()}
+        arrs.update(weight=1.0, mass=me, charge=-qe)
+        extent = {'x': (-2.0, 10.0), 'y': (-5.0, 5.0), 'z': (-4.0, 4.0)}
+        return cls('electron', arrs, extent={k: extent[k] for k in 'xyz'[:dimensions]})
+
     def atomic(self, name):
         if name not in self._arrays:
             raise KeyError(name)

@@ -306,6 +306,20 @@ class TestCreateField:
         f = none.createField('x', 'y', bins=[4, 4], rangex=(-1, 1), rangey=(-1, 1))
         assert f.matrix.shape == (4, 4) and not f.matrix.any()
 
+    def test_dummy_species_host_and_device_agree(self):
+        """test/test_particles.py:37-49 on the reference's own fixture: createField of p + p is twice that
+        of p, for the dummy species on the host and uploaded to the device."""
+        from postpic_b200 import MultiSpecies, ArraySource
+        ph = MultiSpecies(ArraySource.dummy(10000, dimensions=2))
+        pd = MultiSpecies(ArraySource.dummy(10000, dimensions=2, device='cuda:0'))
+        for p in (ph, pd):
+            f1 = p.createField('x', 'y', bins=[50, 40], simextent=True)
+            f2 = (p + p).createField('x', 'y', bins=[50, 40], simextent=True)
+            assert np.allclose(2 * f1.matrix, f2.matrix) and f1.extent == [-2.0, 10.0, -5.0, 5.0]
+        fh = ph.createField('x', 'y', bins=[50, 40], simextent=True, weights='Ekin_MeV', shape=3)
+        fd = pd.createField('x', 'y', bins=[50, 40], simextent=True, weights='Ekin_MeV', shape=3)
+        assert np.allclose(fd.matrix, fh.matrix, rtol=1e-10, atol=1e-12 * np.abs(fh.matrix).max())
+
     def test_empty_and_aliases(self):
         from postpic_b200 import MultiSpecies, ArraySource
         empty = MultiSpecies(ArraySource('none', dict(x=np.empty(0), y=np.empty(0), weight=np.empty(0))))

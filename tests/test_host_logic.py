@@ -202,6 +202,25 @@ def test_multispecies_dispatch_on_cpu_stack(cpu_stack, monkeypatch, oracle):
     assert h.shape == (4,) and not h.any()
 
 
+def test_dummy_species_follows_the_reference_recipe():
+    # datareader/dummy.py:43-61 restated: seeded, independent of the caller's RNG state
+    from postpic_b200 import ArraySource
+    np.random.seed(5)
+    before = np.random.random()
+    np.random.seed(5)
+    src = ArraySource.dummy(10000, dimensions=3, seed=0)
+    assert np.random.random() == before                     # the global RNG is left untouched
+    np.random.seed(0)
+    x, y, z = (np.random.normal(size=10000) for _ in range(3))
+    mc = 9.109383e-31 * 299792458.0
+    assert np.array_equal(src.atomic('x'), x) and np.array_equal(src.atomic('y'), y) and np.array_equal(src.atomic('z'), z)
+    assert np.array_equal(src.atomic('px'), np.roll(x, 1) ** 2 * mc) and np.array_equal(src.atomic('pz'), np.roll(x, 3) * mc)
+    assert np.array_equal(src.atomic('weight'), np.ones(10000)) and len(src) == 10000
+    assert sorted(src.atomic('id')) == list(range(10000))
+    assert src.extent == {'x': (-2.0, 10.0), 'y': (-5.0, 5.0), 'z': (-4.0, 4.0)} and src.species == 'electron'
+    assert set(ArraySource.dummy(10, dimensions=1).extent) == {'x'}
+
+
 def test_shard_bounds_cover_everything():
     from postpic_b200.parallel import shard_bounds
     for n in (0, 1, 7, 8, 1000003):
