@@ -326,7 +326,8 @@ def launches_per_step(method, nd, shape, n, plan):
     if method == "tiled":
         return 2
     if method == "sorted":
-        return 2 + 3 + 2 * nw ** nd            # keys, offsets, ~3 CUB kernels, two reduce launches per colour
+        passes = -(-max(plan.cells.bit_length(), 1) // 8)
+        return 2 + 4 * passes + 2 * nw ** nd   # keys, offsets, 4 sort kernels per 8-bit pass, two reduce launches per colour
     return 1
 
 

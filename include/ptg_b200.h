@@ -198,6 +198,9 @@ int ptg_release(void);
 /* out[i] = the library's division-by-6 of in[i] (device pointers) -- checked bit-for-bit
  * against IEEE division by the tests.                                                   */
 int ptg_selftest_div6(int64_t n, const double *in, double *out, void *stream);
+/* the library's radix sort (method SORTED): keys[0..n) (device, uint32) sorted in place by their low
+ * `bits` bits, stably; perm[i] = original index of the i-th sorted key.                           */
+int ptg_selftest_radix_sort(int64_t n, int bits, unsigned *keys, unsigned *perm, void *stream);
 /* the verdict of the most recent AUTO / TILED probe on the current device (synchronises):
  * mode 0 = ROWS, 1 = TILED, 2 = RUNS, 3 = RUNS_WIDE; ext[3] = tile window extents.          */
 int ptg_debug_last_probe(int *mode, int *ext, float *est_hit, float *run_frac, float *near_frac);

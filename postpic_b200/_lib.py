@@ -77,6 +77,7 @@ SIGNATURES = {
     "ptg_upload_host_f64": (_c.c_int, [_I64, _P, _I64, _P, _c.c_int]),
     "ptg_release": (_c.c_int, []),
     "ptg_selftest_div6": (_c.c_int, [_I64, _P, _P, _P]),
+    "ptg_selftest_radix_sort": (_c.c_int, [_I64, _c.c_int, _P, _P, _P]),
     "ptg_debug_last_probe": (_c.c_int, [_P, _P, _P, _P, _P]),
 }
 

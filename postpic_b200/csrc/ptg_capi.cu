@@ -752,6 +752,16 @@ int ptg_debug_last_probe(int *mode, int *ext, float *est_hit, float *run_frac, f
     return PTG_OK;
 }
 
+int ptg_selftest_radix_sort(int64_t n, int bits, unsigned *keys, unsigned *perm, void *stream) {
+    if (n < 0 || bits < 1 || bits > 32 || n >= (int64_t(1) << 32) || (n > 0 && (!keys || !perm)))
+        return fail(PTG_EINVAL, "ptg_selftest_radix_sort: bad arguments");
+    DeviceState *d;
+    int rc = current_device_state(&d);
+    if (rc) return rc;
+    PTG_CUDA(ptg::selftest_radix_sort(n, bits, keys, perm, (cudaStream_t)stream));
+    return PTG_OK;
+}
+
 int ptg_selftest_div6(int64_t n, const double *in, double *out, void *stream) {
     if (n < 0 || (n > 0 && (!in || !out))) return fail(PTG_EINVAL, "ptg_selftest_div6: bad arguments");
     DeviceState *d;

@@ -2,9 +2,9 @@
 //
 //   1. k_cell_keys      key[i] = padded linear index of particle i's stencil base cell
 //                       (rejected particles get the sentinel key `cells`)
-//   2. stable LSD radix sort of (key, particle index) pairs -- cub::DeviceRadixSort, the
-//      one library call on this path (NVIDIA's CUB ships inside the CUDA toolkit); only
-//      the bits a key can have are sorted
+//   2. stable LSD radix sort of (key, particle index) pairs -- hand-written, 8-bit digits,
+//      match_any-based stable ranking (ptg_radix_sort.cuh); only the bits a key can have are
+//      sorted (3 passes for the 1028^2 grid)
 //   3. k_cell_offsets   CSR offsets: particles of base cell c are idx[off[c] .. off[c+1])
 //                       in ORIGINAL particle order (the sort is stable)
 //   4. k_segment_reduce one launch per stencil "colour" (base cells with equal coordinates
@@ -20,9 +20,8 @@
 //
 // Replaces the loops of /root/reference/postpic/particles/_particlestogrid.pyx
 // :70-129 (1-D), :181-276 (2-D), :341-463 (3-D).
-#include <cub/device/device_radix_sort.cuh>
-
 #include "ptg_internal.cuh"
+#include "ptg_radix_sort.cuh"
 
 namespace ptg {
 
@@ -157,10 +156,9 @@ static int key_bits(uint32_t cells) {
 }
 
 size_t sorted_workspace_bytes(int64_t n, int64_t cells) {
-    // 4 arrays of n u32 (double-buffered keys and indices), offsets, CUB scratch (bounded: with
-    // DoubleBuffer the onesweep scratch is histograms + look-back state, well under 16 MiB + n/64)
+    // 4 arrays of n u32 (double-buffered keys and indices), the CSR offsets, the sort's digit counts
     auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-    return 4 * al((size_t)n * 4) + al((size_t)(cells + 2) * 4) + al((size_t)16 << 20) + al((size_t)n / 16);
+    return 4 * al((size_t)n * 4) + al((size_t)(cells + 2) * 4) + al(radix_sort_scratch_bytes(n));
 }
 
 template <int ND, int S, bool W>
@@ -174,25 +172,21 @@ static cudaError_t run_sorted(const DepositParams &P, void *ws, size_t ws_bytes,
     uint32_t *i0 = reinterpret_cast<uint32_t *>(base); base += al((size_t)P.n * 4);
     uint32_t *i1 = reinterpret_cast<uint32_t *>(base); base += al((size_t)P.n * 4);
     uint32_t *off = reinterpret_cast<uint32_t *>(base); base += al((size_t)(cells + 2) * 4);
-    void *cub_tmp = base;
-    size_t cub_avail = ws_bytes - (size_t)(base - static_cast<char *>(ws));
+    void *sort_scratch = base;
+    if ((size_t)(base - static_cast<char *>(ws)) + radix_sort_scratch_bytes(P.n) > ws_bytes) return cudaErrorMemoryAllocation;
 
     const int64_t cap = (int64_t)sm_count * 8;
     int64_t want = (P.n + 256 * 4 - 1) / (256 * 4);
     int blocks = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     k_cell_keys<ND, S><<<blocks, 256, 0, st>>>(P, cells, k0, i0);
 
-    cub::DoubleBuffer<uint32_t> dk(k0, k1), di(i0, i1);
-    size_t need = 0;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, need, dk, di, P.n, 0, key_bits(cells), st);
-    if (e != cudaSuccess) return e;
-    if (need > cub_avail) return cudaErrorMemoryAllocation;
-    e = cub::DeviceRadixSort::SortPairs(cub_tmp, need, dk, di, P.n, 0, key_bits(cells), st);
+    uint32_t *ks = nullptr, *is = nullptr;       // whichever buffer the last pass wrote
+    cudaError_t e = radix_sort_pairs(k0, k1, i0, i1, P.n, key_bits(cells), sort_scratch, st, &ks, &is);
     if (e != cudaSuccess) return e;
 
     want = (P.n + 1 + 255) / 256;
     blocks = (int)(want < cap ? want : cap);
-    k_cell_offsets<<<blocks, 256, 0, st>>>(dk.Current(), P.n, cells, off);
+    k_cell_offsets<<<blocks, 256, 0, st>>>(ks, P.n, cells, off);
 
     constexpr int NW = StencilWidth<S>::value;
     const int ncx = NW, ncy = ND >= 2 ? NW : 1, ncz = ND >= 3 ? NW : 1;
@@ -205,12 +199,12 @@ static cudaError_t run_sorted(const DepositParams &P, void *ws, size_t ws_bytes,
                 if (ncell <= 0) continue;
                 int64_t wantb = (ncell + 7) / 8;                  // 8 warps per CTA
                 int nb = (int)(wantb < cap * 4 ? wantb : cap * 4);
-                if (W && P.fuse_kind) k_segment_reduce<ND, S, W, false, W><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
-                else k_segment_reduce<ND, S, W, false, false><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
+                if (W && P.fuse_kind) k_segment_reduce<ND, S, W, false, W><<<nb, 256, 0, st>>>(P, is, off, cx, cy, cz);
+                else k_segment_reduce<ND, S, W, false, false><<<nb, 256, 0, st>>>(P, is, off, cx, cy, cz);
                 // the long segments of the same colour (clustered input), one CTA each
                 nb = (int)(ncell < cap ? ncell : cap);
-                if (W && P.fuse_kind) k_segment_reduce<ND, S, W, true, W><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
-                else k_segment_reduce<ND, S, W, true, false><<<nb, 256, 0, st>>>(P, di.Current(), off, cx, cy, cz);
+                if (W && P.fuse_kind) k_segment_reduce<ND, S, W, true, W><<<nb, 256, 0, st>>>(P, is, off, cx, cy, cz);
+                else k_segment_reduce<ND, S, W, true, false><<<nb, 256, 0, st>>>(P, is, off, cx, cy, cz);
             }
     return cudaGetLastError();
 }
@@ -228,6 +222,31 @@ static cudaError_t sorted_s(int shape, const DepositParams &P, void *ws, size_t 
         case 2: return sorted_w<ND, 2>(P, ws, wsb, sm, st);
         default: return sorted_w<ND, 3>(P, ws, wsb, sm, st);
     }
+}
+
+__global__ void k_iota(uint32_t *v, int64_t n) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) v[i] = (uint32_t)i;
+}
+
+// test hook: keys[0..n) sorted in place by their low `bits` bits (stable), perm[i] = original index
+cudaError_t selftest_radix_sort(int64_t n, int bits, uint32_t *keys, uint32_t *perm, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    uint32_t *k1 = nullptr, *v0 = nullptr;
+    void *scratch = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&k1), (size_t)n * 4, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&v0), (size_t)n * 4, st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&scratch, radix_sort_scratch_bytes(n), st);
+    if (e != cudaSuccess) return e;
+    k_iota<<<1024, 256, 0, st>>>(v0, n);
+    uint32_t *ks = nullptr, *vs = nullptr;
+    e = radix_sort_pairs(keys, k1, v0, perm, n, bits, scratch, st, &ks, &vs);
+    if (e == cudaSuccess && ks != keys) e = cudaMemcpyAsync(keys, ks, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess && vs != perm) e = cudaMemcpyAsync(perm, vs, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+    cudaFreeAsync(k1, st);
+    cudaFreeAsync(v0, st);
+    cudaFreeAsync(scratch, st);
+    return e;
 }
 
 cudaError_t deposit_sorted(int ndim, int shape, const DepositParams &P, void *ws, size_t ws_bytes, int sm_count,

@@ -47,6 +47,8 @@ size_t sorted_workspace_bytes(int64_t n, int64_t cells);
 cudaError_t deposit_sorted(int ndim, int shape, const DepositParams &P, void *ws, size_t ws_bytes, int sm_count,
                            cudaStream_t st);
 
+cudaError_t selftest_radix_sort(int64_t n, int bits, uint32_t *keys, uint32_t *perm, cudaStream_t st);
+
 // ptg_util.cu
 cudaError_t minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, int sm_count,
                        cudaStream_t st);

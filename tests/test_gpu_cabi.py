@@ -138,3 +138,23 @@ def test_more_than_2_31_particles(lib):
     grid, plan = device.deposit([x], None, range=(0, 1), bins=1000, shape=1, method=None)
     assert abs(float(grid.sum()) - n) <= 1e-12 * n
     del x
+
+
+@pytest.mark.parametrize("n,bits,maxkey", [(1, 8, 200), (33, 8, 7), (8192, 16, 65535), (8193, 21, 2 ** 21 - 1),
+                                           (1_000_003, 24, 2 ** 21), (5_000_000, 31, 2 ** 31 - 1),
+                                           (3_000_000, 8, 3)])
+def test_radix_sort_is_a_stable_sort(lib, n, bits, maxkey):
+    """The hand-written LSD radix sort of method SORTED against torch's stable sort: same sorted keys,
+    same permutation (equal keys keep their input order)."""
+    import torch
+    from postpic_b200 import _lib
+    g = torch.Generator(device='cuda').manual_seed(n + bits)
+    keys = torch.randint(0, maxkey + 1, (n,), device='cuda', generator=g, dtype=torch.int64)
+    ref_keys, ref_perm = torch.sort(keys, stable=True)
+    k32 = keys.to(torch.int32).contiguous()           # bit pattern of the uint32 keys (all < 2^31 here)
+    perm = torch.empty(n, dtype=torch.int32, device='cuda')
+    _lib.check(lib.ptg_selftest_radix_sort(n, bits, k32.data_ptr(), perm.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert torch.equal(k32.to(torch.int64), ref_keys)
+    assert torch.equal(perm.to(torch.int64), ref_perm)
