@@ -31,19 +31,25 @@ __device__ __forceinline__ unsigned rs_digit(uint32_t key, int shift, bool valid
     return valid ? ((key >> shift) & 255u) : 256u + (unsigned)lane;
 }
 
-// per-warp digit histogram of this warp's slice of the CTA's tile (shared: hist[8][256])
+// per-warp digit histogram of this warp's slice of the CTA's tile (shared: hist[8][256]).  Counting needs
+// no order, so it uses the native 32-bit shared-memory atomic, four rounds of loads in flight at a time.
 __device__ __forceinline__ void rs_count_slice(const uint32_t *keys, int64_t n, int64_t slice0, int shift,
                                                unsigned *hist /* this warp's 256 counters */) {
     const int lane = threadIdx.x & 31;
-    for (int r = 0; r < kRsRounds; ++r) {
-        const int64_t i = slice0 + (int64_t)r * 32 + lane;
-        const bool valid = i < n;
-        const uint32_t key = valid ? keys[i] : 0u;
-        const unsigned d = rs_digit(key, shift, valid, lane);
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        if (valid && (peers & ((1u << lane) - 1u)) == 0u) hist[d] += __popc(peers);   // lowest lane of each group
-        __syncwarp();
+    for (int r = 0; r < kRsRounds; r += 4) {
+        uint32_t key[4];
+        bool valid[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = slice0 + (int64_t)(r + u) * 32 + lane;
+            valid[u] = i < n;
+            key[u] = valid[u] ? keys[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (valid[u]) atomicAdd(&hist[(key[u] >> shift) & 255u], 1u);
     }
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(kRsThreads) k_rs_count(const uint32_t *keys, int64_t n, int shift,
@@ -154,11 +160,16 @@ __global__ void __launch_bounds__(kRsThreads, 3) k_rs_scatter(const uint32_t *ke
     // pass 1: every pair goes to its digit-ordered place inside the tile (shared memory).  The rank of a
     // pair within its round of 32 comes from match_any, lower lanes first: stable.
     unsigned *pos = hist[warp];
+    uint32_t nkey = 0u, nval = 0u;
+    {
+        const int64_t i = slice0 + lane;
+        if (i < n) { nkey = keys_in[i]; nval = vals_in[i]; }
+    }
     for (int r = 0; r < kRsRounds; ++r) {
         const int64_t i = slice0 + (int64_t)r * 32 + lane;
         const bool valid = i < n;
-        const uint32_t key = valid ? keys_in[i] : 0u;
-        const uint32_t val = valid ? vals_in[i] : 0u;
+        const uint32_t key = nkey, val = nval;
+        if (r + 1 < kRsRounds && i + 32 < n) { nkey = keys_in[i + 32]; nval = vals_in[i + 32]; }   // next round in flight
         const unsigned d = rs_digit(key, shift, valid, lane);
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const unsigned below = __popc(peers & ((1u << lane) - 1u));
