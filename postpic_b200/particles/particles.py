@@ -185,10 +185,35 @@ def _torch_funcs():
             'exp': torch.exp, 'log': torch.log, 'abs': torch.abs, 'where': torch.where}
 
 
+class _DeviceGrid(object):
+    """A finished (scaled) ghost-padded grid that still lives in HBM, plus the slice selecting the
+    returned bins.  `host()` is the one device->host copy of the whole path."""
+
+    def __init__(self, padded, interior):
+        self.padded = padded
+        self.interior = interior
+
+    @property
+    def tensor(self):
+        return self.padded[self.interior]
+
+    @property
+    def shape(self):
+        return tuple(self.tensor.shape)
+
+    def host(self):
+        return self.padded.cpu().numpy()[self.interior]
+
+
 class Field(object):
     """Minimal result container with the constructor contract of postpic's `Field`
     (datahandling.py:561-612): `Field(matrix, xedges=..., yedges=..., zedges=...)`
-    keeps `np.asarray(matrix)` and one edge array per axis."""
+    keeps `np.asarray(matrix)` and one edge array per axis.
+
+    SURVEY.md section 8 row f4: a field created from device-resident species keeps its grid in HBM
+    (`device_matrix`, a torch view of the padded grid) and copies it to the host only when `matrix`
+    (or `np.asarray(field)`) is first read, so fields that are only summed, scaled or all-reduced on
+    the device never cross PCIe."""
 
     class _Axis(object):
         def __init__(self, grid_node):
@@ -205,9 +230,12 @@ class Field(object):
             return [self.grid_node[0], self.grid_node[-1]]
 
     def __init__(self, matrix, xedges=None, yedges=None, zedges=None, name='', unit=''):
-        self.matrix = np.asarray(matrix)
+        if isinstance(matrix, _DeviceGrid):
+            self._device_grid, self._matrix = matrix, None
+        else:
+            self._device_grid, self._matrix = None, np.asarray(matrix)
         self.axes = [Field._Axis(e) for e in (xedges, yedges, zedges) if e is not None]
-        if len(self.axes) != self.matrix.ndim:
+        if len(self.axes) != len(self.shape):
             raise ValueError('one edge array per matrix dimension is required')
         self.name = name
         self.unit = unit
@@ -216,12 +244,27 @@ class Field(object):
         self.infos = []
 
     @property
+    def matrix(self):
+        if self._matrix is None:
+            self._matrix = self._device_grid.host()
+        return self._matrix
+
+    @matrix.setter
+    def matrix(self, value):
+        self._device_grid, self._matrix = None, np.asarray(value)
+
+    @property
+    def device_matrix(self):
+        """The histogram as a torch CUDA view (None for fields created from host arrays)."""
+        return None if self._device_grid is None else self._device_grid.tensor
+
+    @property
     def shape(self):
-        return self.matrix.shape
+        return self._device_grid.shape if self._matrix is None else self._matrix.shape
 
     @property
     def dimensions(self):
-        return self.matrix.ndim
+        return len(self.shape)
 
     @property
     def extent(self):
@@ -371,6 +414,7 @@ class MultiSpecies(object):
         force = kwargs.pop('force', False)
         bins = kwargs.pop('bins', None)
         shape = kwargs.pop('shape', None)
+        keep_on_device = kwargs.pop('_keep_on_device', False)      # createField only (row f4)
         if len(kwargs) > 0:
             raise TypeError("got an unexpected keyword argument {}'".format(kwargs))
         if len(sps) > 3:
@@ -408,14 +452,14 @@ class MultiSpecies(object):
             return h, edges
 
         if data is None:
-            return self._createHistgram_per_species(sps, ranges, weights, bins, shape)
+            return self._createHistgram_per_species(sps, ranges, weights, bins, shape, keep_on_device)
         w = self._weights(weights)
         h, edges = histogramdd(data, weights=w, range=ranges, bins=bins, shape=shape)
         dV = np.prod([edge[1] - edge[0] for edge in edges])
         h /= dV
         return h, edges
 
-    def _createHistgram_per_species(self, sps, ranges, weights, bins, shape):
+    def _createHistgram_per_species(self, sps, ranges, weights, bins, shape, keep_on_device=False):
         """Several device-resident species: deposition is linear in the particle set, so every
         species is deposited into the SAME device grid, one after the other, instead of first
         concatenating all per-particle arrays (the np.hstack of particles.py:662-674).  The
@@ -471,6 +515,8 @@ class MultiSpecies(object):
                                  w if (w is None or w.dtype == torch.float64) else w.to(torch.float64), zero=False,
                                  fused=fused, mask=mk)
         _device.scale_(grid, 1.0 / plan.cell_volume())
+        if keep_on_device:
+            return _DeviceGrid(grid, plan.interior), tuple(plan.edges)
         h = grid.cpu().numpy()[plan.interior]
         return h, tuple(plan.edges)
 
@@ -488,7 +534,7 @@ class MultiSpecies(object):
         (particles.py:1105-1167).  Extra keywords: name (default 'distfn'), title."""
         name = kwargs.pop('name', 'distfn')
         title = kwargs.pop('title', None)
-        h, edges = self._createHistgram(*sps, **kwargs)
+        h, edges = self._createHistgram(*sps, _keep_on_device=True, **kwargs)
         edgekw = {k: e for k, e in zip(['xedges', 'yedges', 'zedges'], edges)}
         ret = Field(h, **edgekw)
         if 'weights' in kwargs:

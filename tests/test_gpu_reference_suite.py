@@ -205,7 +205,14 @@ class TestCreateField:
         assert f.name.startswith('Ekin_MeV')
         pd = MultiSpecies(self._species(device='cuda'))
         fd = pd.createField('x', 'y', **kw)
+        # row f4: the finished grid stays in HBM until the host matrix is first read
+        assert f.device_matrix is None
+        assert fd._matrix is None and fd.device_matrix.is_cuda and fd.shape == (64, 64) and fd.dimensions == 2
+        assert np.allclose(fd.device_matrix.cpu().numpy(), f.matrix, rtol=1e-10, atol=1e-300)
         assert np.allclose(fd.matrix, f.matrix, rtol=1e-10, atol=1e-300)
+        assert fd._matrix is not None and np.asarray(fd) is fd.matrix
+        h2, _ = pd._createHistgram('x', 'y', **kw)          # the (h, edges) contract itself stays numpy
+        assert isinstance(h2, np.ndarray) and np.allclose(h2, fd.matrix, rtol=1e-12, atol=1e-300)
 
     @pytest.mark.parametrize("kind", ['gamma_m1', 'gamma', 'Ekin', 'Ekin_MeV', 'Ekin_keV', 'p'])
     def test_fused_kinetic_weights_match_the_expression_chain(self, kind):
