@@ -41,8 +41,9 @@ constexpr int64_t kChunk = int64_t(1) << 22;      // particles per pipeline chun
 constexpr int64_t kStageChunk = int64_t(1) << 21; // ... when staging through pinned memory (16 MiB per array)
 
 struct DeviceState {
-    bool probed = false;
+    std::atomic<bool> probed{false};
     bool usable = false;
+    std::mutex mu;                                // serialises the host-buffer entry points of THIS device
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
     // host-entry staging
@@ -56,12 +57,22 @@ struct DeviceState {
     cudaEvent_t h2d_done[kSlots] = {};
     bool pinned_ready = false;
     // ring of probe verdicts for the TILED / AUTO methods (one entry per call in flight)
-    ptg::TileConfig *cfg_ring = nullptr;
+    std::atomic<ptg::TileConfig *> cfg_ring{nullptr};
     std::atomic<unsigned> cfg_next{0};
 };
 
 DeviceState g_dev[kMaxDevices];
-std::mutex g_mu;
+std::mutex g_mu;          // first-use probing of a device only
+
+// a CUDA event that is destroyed on every exit path
+struct Event {
+    cudaEvent_t e = nullptr;
+    cudaError_t create() { return cudaEventCreateWithFlags(&e, cudaEventDisableTiming); }
+    ~Event() { if (e) cudaEventDestroy(e); }
+    Event() = default;
+    Event(const Event &) = delete;
+    Event &operator=(const Event &) = delete;
+};
 
 int probe(int device, DeviceState **out) {
     if (device < 0) {
@@ -70,9 +81,9 @@ int probe(int device, DeviceState **out) {
     }
     if (device >= kMaxDevices) return fail(PTG_EINVAL, "device index %d too large", device);
     DeviceState &d = g_dev[device];
-    if (!d.probed) {
+    if (!d.probed.load(std::memory_order_acquire)) {
         std::lock_guard<std::mutex> lk(g_mu);
-        if (!d.probed) {
+        if (!d.probed.load(std::memory_order_relaxed)) {
             cudaDeviceProp p;
             cudaError_t e = cudaGetDeviceProperties(&p, device);
             if (e != cudaSuccess) {
@@ -92,7 +103,7 @@ int probe(int device, DeviceState **out) {
                 (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
             }
             (void)cudaGetLastError();
-            d.probed = true;
+            d.probed.store(true, std::memory_order_release);
         }
     }
     if (!d.usable)
@@ -162,19 +173,21 @@ struct MaskSpec {
 // (the host pipeline below never has more than 8).
 constexpr unsigned kCfgRing = 4096;
 
-std::mutex g_ring_mu;     // never held together with g_mu by the same call path in reverse order
+std::mutex g_ring_mu;     // taken while a device mutex may be held, never the other way round
 
 int next_tile_config(DeviceState *d, ptg::TileConfig **out) {
-    if (!d->cfg_ring) {
+    ptg::TileConfig *ring = d->cfg_ring.load(std::memory_order_acquire);
+    if (!ring) {
         std::lock_guard<std::mutex> lk(g_ring_mu);
-        if (!d->cfg_ring) {
-            ptg::TileConfig *ring = nullptr;
+        ring = d->cfg_ring.load(std::memory_order_relaxed);
+        if (!ring) {
             PTG_CUDA(cudaMalloc(&ring, kCfgRing * sizeof(ptg::TileConfig)));
-            PTG_CUDA(cudaMemset(ring, 0, kCfgRing * sizeof(ptg::TileConfig)));   // tickets start at 0
-            d->cfg_ring = ring;
+            cudaError_t e = cudaMemset(ring, 0, kCfgRing * sizeof(ptg::TileConfig));   // tickets start at 0
+            if (e != cudaSuccess) { cudaFree(ring); PTG_CUDA(e); }
+            d->cfg_ring.store(ring, std::memory_order_release);
         }
     }
-    *out = d->cfg_ring + (d->cfg_next.fetch_add(1) % kCfgRing);
+    *out = ring + (d->cfg_next.fetch_add(1) % kCfgRing);
     return PTG_OK;
 }
 
@@ -267,9 +280,9 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
 
 int ensure_staging(DeviceState *d, int64_t cells) {
     if (!d->staged) {
-        for (int k = 0; k < kSlots; ++k) {
-            PTG_CUDA(cudaStreamCreateWithFlags(&d->stream[k], cudaStreamNonBlocking));
-            PTG_CUDA(cudaMalloc(&d->slot[k], (size_t)4 * kChunk * sizeof(double)));
+        for (int k = 0; k < kSlots; ++k) {      // (a call that failed half-way is resumed, not repeated)
+            if (!d->stream[k]) PTG_CUDA(cudaStreamCreateWithFlags(&d->stream[k], cudaStreamNonBlocking));
+            if (!d->slot[k]) PTG_CUDA(cudaMalloc(&d->slot[k], (size_t)4 * kChunk * sizeof(double)));
         }
         d->staged = true;
     }
@@ -292,9 +305,10 @@ cudaError_t h2d_strided(double *dst, const double *src, int64_t stride, int64_t 
 int ensure_pinned(DeviceState *d) {
     if (d->pinned_ready) return PTG_OK;
     for (int k = 0; k < kSlots; ++k) {
-        PTG_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&d->pinned[k]), (size_t)4 * kStageChunk * sizeof(double),
-                               cudaHostAllocDefault));
-        PTG_CUDA(cudaEventCreateWithFlags(&d->h2d_done[k], cudaEventDisableTiming));
+        if (!d->pinned[k])
+            PTG_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&d->pinned[k]), (size_t)4 * kStageChunk * sizeof(double),
+                                   cudaHostAllocDefault));
+        if (!d->h2d_done[k]) PTG_CUDA(cudaEventCreateWithFlags(&d->h2d_done[k], cudaEventDisableTiming));
     }
     d->pinned_ready = true;
     return PTG_OK;
@@ -308,15 +322,13 @@ bool is_pinned(const void *p) {
 }
 
 int staging_threads() {
-    static int t = 0;
-    if (t == 0) {
+    static const int threads = [] {
         const char *e = getenv("PTG_HOST_THREADS");
-        int hw = (int)std::thread::hardware_concurrency();
-        t = e ? atoi(e) : (hw > 16 ? 16 : hw);     // measured on the 16-thread box: 4/8/16 -> 1.14/1.38/1.73 Gp/s
-        if (t < 1) t = 1;
-        if (t > 32) t = 32;
-    }
-    return t;
+        const int hw = (int)std::thread::hardware_concurrency();
+        int t = e ? atoi(e) : (hw > 16 ? 16 : hw);   // measured on the 16-thread box: 4/8/16 -> 1.14/1.38/1.73 Gp/s
+        return t < 1 ? 1 : (t > 32 ? 32 : t);
+    }();
+    return threads;
 }
 
 // dst[k][i] = src[k][i * stride[k]] for i in [0, m), all arrays k, split over worker threads
@@ -533,7 +545,7 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
     if ((rc = guard.enter(device))) return rc;
     DeviceState *d;
     if ((rc = current_device_state(&d))) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(d->mu);
     const int64_t cells = ptg_padded_cells(ndim, shape, bins);
     if ((rc = ensure_staging(d, cells))) return rc;
     // Sources the copy engine can read directly (page-locked, unit stride) are DMA'd from where they
@@ -551,10 +563,10 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
     if (!direct && (rc = ensure_pinned(d))) return rc;
 
     PTG_CUDA(cudaMemsetAsync(d->grid, 0, (size_t)cells * sizeof(double), d->stream[0]));
-    cudaEvent_t zeroed;
-    PTG_CUDA(cudaEventCreateWithFlags(&zeroed, cudaEventDisableTiming));
-    PTG_CUDA(cudaEventRecord(zeroed, d->stream[0]));
-    for (int k = 1; k < kSlots; ++k) PTG_CUDA(cudaStreamWaitEvent(d->stream[k], zeroed, 0));
+    Event zeroed;
+    PTG_CUDA(zeroed.create());
+    PTG_CUDA(cudaEventRecord(zeroed.e, d->stream[0]));
+    for (int k = 1; k < kSlots; ++k) PTG_CUDA(cudaStreamWaitEvent(d->stream[k], zeroed.e, 0));
 
     const double *src[4] = {x, ndim >= 2 ? y : nullptr, ndim >= 3 ? z : nullptr, w};
     const unsigned dflags = flags & ~PTG_ZERO_GRID;
@@ -565,14 +577,13 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
     bool slot_used[kSlots] = {};
     // bound the work queued ahead of the GPU: chunk c is only enqueued once chunk c - 8 has finished
     constexpr int kInFlight = 8;
-    cudaEvent_t fin[kInFlight];
-    for (int k = 0; k < kInFlight; ++k) PTG_CUDA(cudaEventCreateWithFlags(&fin[k], cudaEventDisableTiming));
-    struct FinGuard { cudaEvent_t *e; ~FinGuard() { for (int k = 0; k < kInFlight; ++k) cudaEventDestroy(e[k]); } } fin_guard{fin};
+    Event fin[kInFlight];
+    for (int k = 0; k < kInFlight; ++k) PTG_CUDA(fin[k].create());
     int64_t cidx = 0;
     for (int64_t off = 0; off < n; off += chunk, slot = (slot + 1) % kSlots, ++cidx) {
         const int64_t m = n - off < chunk ? n - off : chunk;
         cudaStream_t st = ordered ? d->stream[0] : d->stream[slot];
-        if (cidx >= kInFlight) PTG_CUDA(cudaEventSynchronize(fin[cidx % kInFlight]));
+        if (cidx >= kInFlight) PTG_CUDA(cudaEventSynchronize(fin[cidx % kInFlight].e));
         double *dptr[4] = {nullptr, nullptr, nullptr, nullptr};
         if (direct) {
             for (int k = 0; k < 4; ++k) {
@@ -600,20 +611,18 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
         }
         rc = deposit_device(d, ndim, shape, m, dptr[0], dptr[1], dptr[2], dptr[3], nullptr, lo, inv, bins,
                             d->grid, dflags, st);
-        if (rc) { cudaEventDestroy(zeroed); return rc; }
-        PTG_CUDA(cudaEventRecord(fin[cidx % kInFlight], st));
+        if (rc) return rc;
+        PTG_CUDA(cudaEventRecord(fin[cidx % kInFlight].e, st));
     }
     // join the ring on stream 0, then bring the padded grid home
     for (int k = 1; k < kSlots; ++k) {
-        cudaEvent_t done;
-        PTG_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-        PTG_CUDA(cudaEventRecord(done, d->stream[k]));
-        PTG_CUDA(cudaStreamWaitEvent(d->stream[0], done, 0));
-        PTG_CUDA(cudaEventDestroy(done));
+        Event done;
+        PTG_CUDA(done.create());
+        PTG_CUDA(cudaEventRecord(done.e, d->stream[k]));
+        PTG_CUDA(cudaStreamWaitEvent(d->stream[0], done.e, 0));
     }
     PTG_CUDA(cudaMemcpyAsync(grid, d->grid, (size_t)cells * sizeof(double), cudaMemcpyDeviceToHost, d->stream[0]));
     PTG_CUDA(cudaStreamSynchronize(d->stream[0]));
-    PTG_CUDA(cudaEventDestroy(zeroed));
     return PTG_OK;
 }
 
@@ -624,7 +633,7 @@ int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2
     if (rc) return rc;
     DeviceState *d;
     if ((rc = current_device_state(&d))) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(d->mu);
     if ((rc = ensure_staging(d, 1))) return rc;
     // page-locked unit-stride memory is DMA'd in place, anything else goes through the pinned ring
     const bool direct = stride == 1 && n > 0 && is_pinned(x);
@@ -636,6 +645,7 @@ int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2
     // every chunk is reduced on the device into its own (min, max) pair; the pairs come home in ONE copy
     double *partials = nullptr;
     PTG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&partials), (size_t)nchunks * 16, d->stream[0]));
+    struct Scratch { double *p; cudaStream_t st; ~Scratch() { cudaFreeAsync(p, st); } } scratch{partials, d->stream[0]};
     PTG_CUDA(cudaStreamSynchronize(d->stream[0]));         // the other ring streams may use it right away
     bool slot_used[kSlots] = {};
     int slot = 0;
@@ -660,7 +670,6 @@ int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2
     for (int k = 0; k < kSlots; ++k) PTG_CUDA(cudaStreamSynchronize(d->stream[k]));
     std::vector<double> host((size_t)nchunks * 2);
     PTG_CUDA(cudaMemcpy(host.data(), partials, (size_t)nchunks * 16, cudaMemcpyDeviceToHost));
-    PTG_CUDA(cudaFreeAsync(partials, d->stream[0]));
     double lo = INFINITY, hi = -INFINITY;
     bool nan = false;
     for (int64_t k = 0; k < nchunks; ++k) {
@@ -681,7 +690,7 @@ int ptg_upload_host_f64(int64_t n, const double *src, int64_t stride, double *ds
     if (rc) return rc;
     DeviceState *d;
     if ((rc = current_device_state(&d))) return rc;
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(d->mu);
     if ((rc = ensure_staging(d, 1))) return rc;
     const bool direct = stride == 1 && n > 0 && is_pinned(src);
     if (direct) {
@@ -710,13 +719,15 @@ int ptg_upload_host_f64(int64_t n, const double *src, int64_t stride, double *ds
 }
 
 int ptg_release(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
     int prev = -1;
     if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); return PTG_OK; }
     for (int dev = 0; dev < kMaxDevices; ++dev) {
         DeviceState &d = g_dev[dev];
-        if (!d.staged && !d.grid && !d.cfg_ring) continue;
+        std::lock_guard<std::mutex> lk(d.mu);
+        std::lock_guard<std::mutex> lk_ring(g_ring_mu);
+        if (!d.staged && !d.stream[0] && !d.grid && !d.cfg_ring.load()) continue;
         cudaSetDevice(dev);
+        cudaDeviceSynchronize();                  // nothing of this device may still read what is freed below
         for (int k = 0; k < kSlots; ++k) {
             if (d.slot[k]) cudaFree(d.slot[k]);
             if (d.stream[k]) cudaStreamDestroy(d.stream[k]);
@@ -728,8 +739,8 @@ int ptg_release(void) {
             d.stream[k] = nullptr;
         }
         if (d.grid) cudaFree(d.grid);
-        if (d.cfg_ring) cudaFree(d.cfg_ring);
-        d.cfg_ring = nullptr;
+        if (d.cfg_ring.load()) cudaFree(d.cfg_ring.load());
+        d.cfg_ring.store(nullptr);
         d.grid = nullptr; d.grid_cells = 0; d.staged = false; d.pinned_ready = false;
     }
     cudaSetDevice(prev);
@@ -740,10 +751,10 @@ int ptg_debug_last_probe(int *mode, int *ext, float *est_hit, float *run_frac, f
     DeviceState *d;
     int rc = current_device_state(&d);
     if (rc) return rc;
-    if (!d->cfg_ring || d->cfg_next.load() == 0) return fail(PTG_EINVAL, "no AUTO/TILED call has been made on this device yet");
+    if (!d->cfg_ring.load() || d->cfg_next.load() == 0) return fail(PTG_EINVAL, "no AUTO/TILED call has been made on this device yet");
     ptg::TileConfig c;
     PTG_CUDA(cudaDeviceSynchronize());
-    PTG_CUDA(cudaMemcpy(&c, d->cfg_ring + ((d->cfg_next.load() - 1) % kCfgRing), sizeof c, cudaMemcpyDeviceToHost));
+    PTG_CUDA(cudaMemcpy(&c, d->cfg_ring.load() + ((d->cfg_next.load() - 1) % kCfgRing), sizeof c, cudaMemcpyDeviceToHost));
     if (mode) *mode = c.mode;
     if (ext) for (int a = 0; a < 3; ++a) ext[a] = c.ext[a];
     if (est_hit) *est_hit = c.est_hit;

@@ -87,6 +87,8 @@ def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, strea
         _check_tensor(weights, 'weights')
         if weights.numel() < n:
             raise ValueError('weights must have at least as many elements as data')
+        if weights.device != grid.device:
+            raise ValueError('all tensors must live on the same device')
     if grid.dtype != torch.float64 or not grid.is_contiguous() or grid.numel() != plan.cells:
         raise ValueError('grid must be a contiguous float64 tensor of {} elements'.format(plan.cells))
     ptr = [t.data_ptr() if n else None for t in coords] + [None] * (3 - plan.ndim)
@@ -95,6 +97,13 @@ def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, strea
     strides.append(weights.stride(0) if (weights is not None and n > 1) else 1)
     cstr = (ctypes.c_int64 * 4)(*strides)
     flags = _lib.METHODS[method] | (_lib.ZERO_GRID if zero else 0)
+    if fused is not None:
+        q = [fused['px'], fused['py'], fused['pz']]
+        for t, nm in zip(q, ('px', 'py', 'pz')):
+            _check_tensor(t, nm)
+            if t.numel() < n or t.device != grid.device:
+                raise ValueError('fused momentum arrays must match the coordinates')
+        qstr = (ctypes.c_int64 * 3)(*[t.stride(0) if n > 1 else 1 for t in q])
     if mask is not None:
         if mask.dtype not in (torch.bool, torch.uint8) or mask.dim() != 1 or mask.numel() < n or \
                 mask.device != grid.device:
@@ -108,13 +117,7 @@ def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, strea
         args.bins = ctypes.cast(plan.cbins, ctypes.c_void_p)
         args.grid, args.flags = grid.data_ptr(), flags
         args.mask, args.mask_stride = (mask.data_ptr() if n else None), (mask.stride(0) if n > 1 else 1)
-        keep = []
         if fused is not None:
-            q = [fused['px'], fused['py'], fused['pz']]
-            for t, nm in zip(q, ('px', 'py', 'pz')):
-                _check_tensor(t, nm)
-            qstr = (ctypes.c_int64 * 3)(*[t.stride(0) if n > 1 else 1 for t in q])
-            keep.append(qstr)
             args.fuse_kind = WEIGHT_KINDS[fused['kind']]
             args.px, args.py, args.pz = (t.data_ptr() if n else None for t in q)
             args.pstrides = ctypes.cast(qstr, ctypes.c_void_p)
@@ -132,12 +135,6 @@ def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, strea
                                            plan.lo.ctypes.data, plan.inv.ctypes.data, plan.cbins,
                                            grid.data_ptr(), flags, None, 0, st))
         else:
-            q = [fused['px'], fused['py'], fused['pz']]
-            for t, nm in zip(q, ('px', 'py', 'pz')):
-                _check_tensor(t, nm)
-                if t.numel() < n or t.device != grid.device:
-                    raise ValueError('fused momentum arrays must match the coordinates')
-            qstr = (ctypes.c_int64 * 3)(*[t.stride(0) if n > 1 else 1 for t in q])
             _lib.check(lib.ptg_deposit_fused_f64(
                 plan.ndim, plan.shape, n, ptr[0], ptr[1], ptr[2], ptr[3], cstr, plan.lo.ctypes.data,
                 plan.inv.ctypes.data, plan.cbins, grid.data_ptr(), flags, WEIGHT_KINDS[fused['kind']],
