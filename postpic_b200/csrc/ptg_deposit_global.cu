@@ -194,6 +194,88 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
     }
 }
 
+// The same sector-coalesced reductions without the shared-memory transposition: G adjacent lanes
+// share ONE particle -- each of them loads it (a broadcast within the request), evaluates its stencil
+// and keeps only the last-axis weight of its own cell j -- so the lanes of a RED instruction cover
+// whole stencil rows by construction.  The arithmetic is done G times over, on the FP64 pipe that
+// this path leaves idle; what it saves is the l1tex bandwidth of the staging stores and loads,
+// which share a pipeline with the reductions (ncu: 54 shared-memory wavefronts per 32 particles next
+// to 96 sector-cycles of REDs).  No warp-level exchange at all, hence no convergence constraints.
+constexpr int kQuadUnroll = 2;
+template <int ND, int S, bool W, bool STAG, bool F>
+__global__ void __launch_bounds__(kThreads) k_deposit_quads(const DepositParams P, const TileConfig *gate) {
+    if (gate != nullptr && gate->mode != kModeRows) return;
+    using C = RowsCfg<ND, S>;
+    constexpr int NW = C::NW, G = C::G, U = kQuadUnroll;
+    constexpr int kGroups = kThreads / G;                             // particles per CTA per step
+    const int j = threadIdx.x % G, group = threadIdx.x / G;
+
+    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2];
+    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2];
+    const int pitch = STAG ? P.stag_pitch : P.dims[ND - 1];
+    const int64_t row_stride = ND == 1 ? 0 : pitch;
+    const int64_t slab_stride = ND == 3 ? (int64_t)P.dims[1] * pitch : 0;
+    double *const target = STAG ? P.stag : P.grid;
+
+    const int64_t span = ((P.n + gridDim.x - 1) / gridDim.x + kGroups - 1) / kGroups * kGroups;
+    const int64_t begin = (int64_t)blockIdx.x * span;
+    const int64_t end = begin + span < P.n ? begin + span : P.n;
+    for (int64_t i0 = begin + group; i0 < end; i0 += (int64_t)kGroups * U) {
+        double x[U], y[U], z[U], w[U];
+        bool live[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + (int64_t)u * kGroups;
+            live[u] = i < end && particle_selected(P, i);
+            x[u] = y[u] = z[u] = 0.0;
+            w[u] = 1.0;
+            if (live[u]) {
+                x[u] = ld_stream(px + i * sx);
+                if (ND >= 2) y[u] = ld_stream(py + i * sy);
+                if (ND >= 3) z[u] = ld_stream(pz + i * sz);
+                if (W) w[u] = particle_weight<F>(P, i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            double wx[NW], wy[NW], wz[NW];
+            int b[3];
+            const bool ok = live[u] && particle_stencil<ND, S>(P, x[u], y[u], z[u], b, wx, wy, wz) &&
+                            b[0] >= P.slab_lo && b[0] < P.slab_hi;
+            if (!ok || j >= NW) continue;
+            const int col = ND == 1 ? b[0] : ND == 2 ? b[1] : b[2];
+            const int rowlin = ND == 1 ? 0 : ND == 2 ? b[0] : b[0] * P.dims[1] + b[1];
+            int64_t lin = (int64_t)rowlin * pitch + col + j;
+            if (STAG) {
+                const bool second = NW == 3 ? (col & 2) != 0 : (col & 3) == 3;
+                if (second) lin += P.stag_copy + 2;
+            }
+            // the last-axis weight of this lane's cell
+            const double (&wl)[NW] = ND == 1 ? wx : ND == 2 ? wy : wz;
+            double wj = wl[0];
+#pragma unroll
+            for (int k = 1; k < NW; ++k) wj = j == k ? wl[k] : wj;
+            if (ND == 1) {
+                red_add(target + lin, W ? __dmul_rn(wj, w[u]) : wj);
+            } else if (ND == 2) {
+#pragma unroll
+                for (int a = 0; a < NW; ++a) {
+                    const double c = __dmul_rn(wx[a], wj);
+                    red_add(target + lin + a * row_stride, W ? __dmul_rn(c, w[u]) : c);
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < NW; ++a)
+#pragma unroll
+                    for (int bb = 0; bb < NW; ++bb) {
+                        const double c = __dmul_rn(__dmul_rn(wx[a], wy[bb]), wj);
+                        red_add(target + lin + a * slab_stride + bb * row_stride, W ? __dmul_rn(c, w[u]) : c);
+                    }
+            }
+        }
+    }
+}
+
 // grid[r][j] += stag0[r][j] + stag1[r][j + 2]   (rows = product of all but the last axis)
 __global__ void __launch_bounds__(256) k_merge_staggered(const DepositParams P, int64_t rows, int last,
                                                           const TileConfig *gate) {
@@ -230,9 +312,18 @@ static cudaError_t launch_rows(const DepositParams &P, const TileConfig *gate, i
     int64_t cap = (int64_t)sm_count * 8;
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
+    // lane-group kernel for rows of 2 or 3 cells in 2-D / 3-D (measured against the staged kernel on cfg2-like
+    // input: CIC 75.5 vs 68.1, TSC 50.5 vs 49.6, 3-D CIC 23.3 vs 20.9 Gp/s; spline3 28.0 vs 29.6, so rows
+    // of 4 stay staged, and so do the fused-weight variants whose sqrt/divide chain would run G times over).
+    // PTG_ROWS_IMPL=q|s forces one of them (A/B runs).
+    static const int forced = [] { const char *e = getenv("PTG_ROWS_IMPL"); return !e ? 0 : e[0] == 'q' ? 1 : 2; }();
+    const bool quads = forced ? forced == 1 : (ND >= 2 && (S == 1 || S == 2) && !(W && P.fuse_kind));
     if (P.stag != nullptr) {
         if constexpr (S == 1 || S == 2) {
-            if (W && P.fuse_kind) k_deposit_rows<ND, S, W, true, W><<<blocks, kThreads, 0, st>>>(P, gate);
+            if (quads) {
+                if (W && P.fuse_kind) k_deposit_quads<ND, S, W, true, W><<<blocks, kThreads, 0, st>>>(P, gate);
+                else k_deposit_quads<ND, S, W, true, false><<<blocks, kThreads, 0, st>>>(P, gate);
+            } else if (W && P.fuse_kind) k_deposit_rows<ND, S, W, true, W><<<blocks, kThreads, 0, st>>>(P, gate);
             else k_deposit_rows<ND, S, W, true, false><<<blocks, kThreads, 0, st>>>(P, gate);
             const int last = P.dims[ND - 1];
             const int64_t rows = (int64_t)P.dims[0] * P.dims[1] * P.dims[2] / last;
@@ -241,7 +332,10 @@ static cudaError_t launch_rows(const DepositParams &P, const TileConfig *gate, i
             return cudaGetLastError();
         }
     }
-    if (W && P.fuse_kind) k_deposit_rows<ND, S, W, false, W><<<blocks, kThreads, 0, st>>>(P, gate);
+    if (quads) {
+        if (W && P.fuse_kind) k_deposit_quads<ND, S, W, false, W><<<blocks, kThreads, 0, st>>>(P, gate);
+        else k_deposit_quads<ND, S, W, false, false><<<blocks, kThreads, 0, st>>>(P, gate);
+    } else if (W && P.fuse_kind) k_deposit_rows<ND, S, W, false, W><<<blocks, kThreads, 0, st>>>(P, gate);
     else k_deposit_rows<ND, S, W, false, false><<<blocks, kThreads, 0, st>>>(P, gate);
     return cudaGetLastError();
 }
