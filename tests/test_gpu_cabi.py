@@ -121,6 +121,54 @@ def test_concurrent_streams_into_one_grid(lib):
             assert float((grid - whole).abs().max()) <= 1e-12 * float(whole.abs().max())
 
 
+def test_host_entries_from_several_threads(oracle):
+    """The host-buffer entry points share one staging ring per device and serialise on a per-device
+    mutex; ctypes releases the GIL, so Python threads really do call them concurrently.  Every thread
+    must get the histogram of ITS data (different shapes, sizes and dimensionalities per thread)."""
+    import threading
+    import postpic_b200.particles._particlestogrid as ptg
+    from postpic_b200 import histogramdd
+    rng = np.random.default_rng(21)
+    jobs = []
+    for t in range(6):
+        n = 200000 + 50000 * t
+        shape = t % 4
+        if t % 2:
+            data = (rng.uniform(0, 1, n), rng.uniform(-1, 1, n))
+            kw = dict(range=((0, 1), (-1, 1)), bins=(64 + t, 48), shape=shape, weights=rng.uniform(0, 1, n))
+            want = oracle.histogram2d(data[0], data[1], **kw)[0]
+        else:
+            data = (rng.normal(0, 1, n),)
+            kw = dict(range=(-3, 3), bins=200 + t, shape=shape, weights=rng.uniform(0, 1, n))
+            want = oracle.histogram(data[0], **kw)[0]
+        jobs.append((data, kw, want))
+    big = rng.normal(0, 1, (1 << 20) + 777)           # large enough for the device min/max + upload route
+    got = [None] * len(jobs)
+    errors = []
+
+    def run(k):
+        try:
+            for _ in range(3):
+                data, kw, _ = jobs[k]
+                got[k] = (ptg.histogram2d(data[0], data[1], **kw) if len(data) == 2 else ptg.histogram(data[0], **kw))[0]
+            # the range-less route (min/max + upload through the same ring) from a thread as well
+            if len(jobs[k][0]) == 1:
+                h, _ = histogramdd(big, bins=50, shape=0)
+                assert h.sum() == big.size - 2                    # strict edges drop the min and the max
+        except Exception as e:                                    # pragma: no cover
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(k,)) for k in range(len(jobs))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=120)
+    assert not errors, errors
+    for (data, kw, want), h in zip(jobs, got):
+        assert h is not None and h.shape == want.shape
+        assert np.max(np.abs(h - want)) <= 1e-12 * np.max(np.abs(want))
+
+
 def test_more_than_2_31_particles(lib):
     """The reference's `cdef int n` overflows at 2^31 particles; here indices are 64-bit.
     1-D, unweighted, shape 0: every particle must be counted exactly once (17 GB of input)."""
