@@ -18,9 +18,13 @@
 //
 // Replaces the loops of /root/reference/postpic/particles/_particlestogrid.pyx
 // :70-129 (1-D), :181-276 (2-D), :341-463 (3-D).
+#include <cstdlib>
+
 #include "ptg_internal.cuh"
 
 namespace ptg {
+
+// PTG_RUNS_IMPL=b|v forces the bulk-copy / the vector-load kernel wherever it exists (A/B runs, tests)
 
 #ifndef PTG_RUNS_MERGE_MAX_HEADS
 #define PTG_RUNS_MERGE_MAX_HEADS 20      // warp merge only when the 32 lanes hold at most this many runs
@@ -60,6 +64,51 @@ __device__ __forceinline__ void load_k(const double *base, int64_t stride, int64
     }
 }
 
+// One run's window -> the grid.  key = padded linear index of the window's first cell.  In a widened window
+// exact zeros are skipped: they carry nothing, and the outermost cells may lie beyond the grid (they can
+// only ever hold zero there).
+template <int MA, int MC, int MD, bool SKIP_ZERO, int MV>
+__device__ __forceinline__ void runs_commit(double *grid, int64_t g1, int64_t g2, int key, const double (&acc)[MV]) {
+    double *g = grid + key;
+#pragma unroll
+    for (int a = 0; a < MA; ++a)
+#pragma unroll
+        for (int c = 0; c < MC; ++c)
+#pragma unroll
+            for (int d = 0; d < MD; ++d) {
+                const double v = acc[(a * MC + c) * MD + d];
+                if (!SKIP_ZERO || v != 0.0) red_add(g + (a * g1 + c) * g2 + d, v);
+            }
+}
+
+// Merge the runs still open at the end of each lane's particles across the warp (segmented shuffle
+// reduction over lanes holding the same window); returns whether this lane has to commit its acc.
+template <int MV>
+__device__ __forceinline__ bool runs_warp_merge(int cur, double (&acc)[MV], int lane) {
+    const int key = cur >= 0 ? cur : -1 - lane;
+    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+    const bool head = lane == 0 || prev != key;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    bool mine = cur >= 0;
+    if (__popc(heads) <= PTG_RUNS_MERGE_MAX_HEADS) {
+        const unsigned above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
+        const int next_head = above ? __ffs(above) - 1 : 32;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const bool take = lane + dd < next_head;
+#pragma unroll
+            for (int k = 0; k < MV; ++k) {
+                const double o = __shfl_down_sync(0xffffffffu, acc[k], dd);
+                // predicated add (one @P DADD) instead of the add + two 32-bit selects nvcc emits
+                asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}"
+                    : "+d"(acc[k]) : "d"(o), "r"((int)take));
+            }
+        }
+        mine = mine && head;
+    }
+    return mine;
+}
+
 // resident CTAs per SM asked of ptxas: 4 (64 registers) for register windows of up to 9 cells
 template <int ND, int S, int WD> struct RunsMinBlocks {
     static constexpr int MW = StencilWidth<S>::value + WD;
@@ -79,21 +128,7 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
     const int lane = threadIdx.x & 31;
     const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
 
-    auto commit = [&](int key, const double (&acc)[MV]) {
-        // key = padded linear index of the window's first cell.  Exact zeros are skipped: they
-        // carry nothing, and the outermost cells of a widened window may lie beyond the grid
-        // (they can only ever hold zero there).
-        double *g = P.grid + key;
-#pragma unroll
-        for (int a = 0; a < MA; ++a)
-#pragma unroll
-            for (int c = 0; c < MC; ++c)
-#pragma unroll
-                for (int d = 0; d < MD; ++d) {
-                    const double v = acc[(a * MC + c) * MD + d];
-                    if (!WD || v != 0.0) red_add(g + (a * g1 + c) * g2 + d, v);
-                }
-    };
+    auto commit = [&](int key, const double (&acc)[MV]) { runs_commit<MA, MC, MD, WD != 0>(P.grid, g1, g2, key, acc); };
 
     // contiguous span per CTA so that concurrently running CTAs work on different grid regions
     const int64_t per_cta = ((P.n + gridDim.x - 1) / gridDim.x + kRT * kRK * kRB - 1) / (kRT * kRK * kRB) * (kRT * kRK * kRB);
@@ -202,30 +237,229 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
                         }
             }
         }
-        // merge the runs still open at the end of each lane's particles across the warp
-        const int key = cur >= 0 ? cur : -1 - lane;
-        const int prev = __shfl_up_sync(0xffffffffu, key, 1);
-        const bool head = lane == 0 || prev != key;
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        bool mine = cur >= 0;
-        if (__popc(heads) <= PTG_RUNS_MERGE_MAX_HEADS) {
-            const unsigned above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
-            const int next_head = above ? __ffs(above) - 1 : 32;
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const bool take = lane + dd < next_head;
-#pragma unroll
-                for (int k = 0; k < MV; ++k) {
-                    const double o = __shfl_down_sync(0xffffffffu, acc[k], dd);
-                    // predicated add (one @P DADD) instead of the add + two 32-bit selects nvcc emits
-                    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}"
-                        : "+d"(acc[k]) : "d"(o), "r"((int)take));
-                }
-            }
-            mine = mine && head;
-        }
-        if (mine) commit(cur, acc);
+        if (runs_warp_merge<MV>(cur, acc, lane)) commit(cur, acc);
     }
+}
+
+// ---------------------------------------------------------------------------------
+// RUNS with the particle stream decoupled from the arithmetic: every warp owns a ring of shared-memory
+// tiles that the copy engine fills with 1-D bulk copies (cp.async.bulk, completion counted in bytes on an
+// mbarrier), kBulkStages tiles ahead.  A tile is 256 consecutive particles (2 KB per array); lane l takes
+// particles [8 l, 8 l + 8) of it into registers with four 128-bit shared loads per array (granules in a
+// lane-rotated order, so the eight lanes of a 128-bit phase fall on eight different bank groups), the
+// slot is handed back to the copy engine at once, and the run accumulation / warp merge / commit are
+// those of k_deposit_runs.  No load instruction waits on HBM any more: the only thing a warp can stall
+// on is a tile that has not landed.
+// ---------------------------------------------------------------------------------
+#ifndef PTG_BULK_PER
+#define PTG_BULK_PER 8
+#endif
+#ifndef PTG_BULK_WARPS
+#define PTG_BULK_WARPS 16
+#endif
+#ifndef PTG_BULK_STAGES
+#define PTG_BULK_STAGES 2
+#endif
+#ifndef PTG_BULK_INTERLEAVE
+#define PTG_BULK_INTERLEAVE 0
+#endif
+constexpr int kBulkPer = PTG_BULK_PER;           // consecutive particles per lane and tile
+constexpr int kBulkTile = 32 * kBulkPer;         // particles per warp tile
+template <int ND, bool W> struct BulkCfg {
+    static constexpr int NA = ND + (W ? 1 : 0);                         // arrays streamed
+    static constexpr int STAGES = NA <= 2 ? PTG_BULK_STAGES + 1 : PTG_BULK_STAGES;
+    static constexpr int TILE_BYTES = NA * kBulkTile * 8;               // one stage of one warp
+    static constexpr int FIT = (200 * 1024) / (STAGES * TILE_BYTES) / 4 * 4;
+    static constexpr int WARPS = FIT >= PTG_BULK_WARPS ? PTG_BULK_WARPS : FIT;
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr size_t SMEM = (size_t)WARPS * STAGES * (TILE_BYTES + 8);
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); the particle
+// stream is touched once: evict-first in L2
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    const uint32_t a = smem_u32(bar);
+    unsigned done = 0;
+    for (unsigned spins = 0; !done; ++spins) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (spins > (1u << 28)) __trap();            // a tile that never lands is a bug, not a reason to hang the GPU
+    }
+}
+
+template <int ND, int S, bool W>
+__global__ void __launch_bounds__(BulkCfg<ND, W>::THREADS, 1) k_deposit_runs_bulk(const DepositParams P, const TileConfig *gate) {
+    if (gate != nullptr && gate->mode != kModeRuns) return;
+    using C = BulkCfg<ND, W>;
+    constexpr int NW = StencilWidth<S>::value;
+    constexpr int MA = NW, MC = ND >= 2 ? NW : 1, MD = ND >= 3 ? NW : 1, MV = MA * MC * MD;
+    constexpr int NA = C::NA, STAGES = C::STAGES;
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *const ring = reinterpret_cast<double *>(bulk_smem) + (size_t)warp * STAGES * NA * kBulkTile;
+    uint64_t *const bars = reinterpret_cast<uint64_t *>(bulk_smem + (size_t)C::WARPS * STAGES * C::TILE_BYTES) + warp * STAGES;
+    const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+
+    // every warp owns a contiguous range of whole tiles
+    const int64_t n_tiles = P.n / kBulkTile;
+    const int64_t gw = (int64_t)blockIdx.x * C::WARPS + warp, GW = (int64_t)gridDim.x * C::WARPS;
+#if PTG_BULK_INTERLEAVE
+    // the warps of a CTA take adjacent tiles in turn: the CTA streams one contiguous range
+    const int64_t per_cta = ((n_tiles + gridDim.x - 1) / gridDim.x + C::WARPS - 1) / C::WARPS * C::WARPS;
+    const int64_t c_begin = (int64_t)blockIdx.x * per_cta < n_tiles ? (int64_t)blockIdx.x * per_cta : n_tiles;
+    const int64_t c_end = c_begin + per_cta < n_tiles ? c_begin + per_cta : n_tiles;
+    constexpr int64_t t_step = C::WARPS;
+    const int64_t t_begin = c_begin + warp < c_end ? c_begin + warp : c_end;
+    const int64_t t_end = c_end;
+#else
+    const int64_t per_warp = (n_tiles + GW - 1) / GW;
+    constexpr int64_t t_step = 1;
+    const int64_t t_begin = gw * per_warp < n_tiles ? gw * per_warp : n_tiles;
+    const int64_t t_end = t_begin + per_warp < n_tiles ? t_begin + per_warp : n_tiles;
+#endif
+
+    auto issue = [&](int64_t t, int s) {                     // lane 0 only
+        mbar_expect_tx(bars + s, (unsigned)C::TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            const double *src = (a < ND ? P.p[a] : P.p[3]) + t * kBulkTile;
+            bulk_load(ring + ((size_t)s * NA + a) * kBulkTile, src, kBulkTile * 8, bars + s);
+        }
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            if (t_begin + s * t_step < t_end) issue(t_begin + s * t_step, s);
+    }
+
+    for (int64_t t = t_begin; t < t_end; t += t_step) {
+        const int64_t k = (t - t_begin) / t_step;
+        const int s = (int)(k % STAGES);
+        mbar_wait(bars + s, (unsigned)((k / STAGES) & 1));
+        // this lane's particles -> registers (granule order rotated by lane: conflict-free 128-bit phases)
+        double v[NA][kBulkPer];
+        const double *mine = ring + (size_t)s * NA * kBulkTile + lane * kBulkPer;
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int q = 0; q < kBulkPer / 2; ++q) {
+                const int gq = (q + lane * kBulkPer / 16) & (kBulkPer / 2 - 1);
+                const double2 two = *reinterpret_cast<const double2 *>(mine + a * kBulkTile + 2 * gq);
+                v[a][2 * q] = two.x;
+                v[a][2 * q + 1] = two.y;
+            }
+        __syncwarp();                                        // every lane has its copy: the slot is free again
+        if (lane == 0 && t + STAGES * t_step < t_end) issue(t + STAGES * t_step, s);
+
+        int cur = -1;
+        double acc[MV];
+#pragma unroll
+        for (int i = 0; i < MV; ++i) acc[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < kBulkPer; ++j) {
+            int b[3];
+            double wx[NW], wy[NW], wz[NW];
+            const double y = ND >= 2 ? v[ND >= 2 ? 1 : 0][j] : 0.0, z = ND >= 3 ? v[ND >= 3 ? 2 : 0][j] : 0.0;
+            if (!particle_stencil<ND, S>(P, v[0][j], y, z, b, wx, wy, wz)) continue;
+            const double wj = W ? v[NA - 1][j] : 1.0;
+            const int key = (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2];            // dims beyond ndim are 1
+            if (key != cur) {                // rare on cell-ordered input: close the run, open a new one
+                if (cur >= 0) runs_commit<MA, MC, MD, false>(P.grid, g1, g2, cur, acc);
+                cur = key;
+#pragma unroll
+                for (int i = 0; i < MV; ++i) acc[i] = 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < MA; ++a)
+#pragma unroll
+                for (int c = 0; c < MC; ++c)
+#pragma unroll
+                    for (int d = 0; d < MD; ++d) {
+                        const int i = (a * MC + c) * MD + d;
+                        acc[i] = __dadd_rn(acc[i], stencil_value<ND, S, W>(wx, wy, wz, a, c, d, wj));
+                    }
+        }
+        if (runs_warp_merge<MV>(cur, acc, lane)) runs_commit<MA, MC, MD, false>(P.grid, g1, g2, cur, acc);
+    }
+
+    // the particles behind the last whole tile (< 256): one per lane, straight to the grid
+    if (gw == 0) {
+        for (int64_t i = n_tiles * kBulkTile + lane; i < P.n; i += 32) {
+            int b[3];
+            double wx[NW], wy[NW], wz[NW];
+            const double x = P.p[0][i], y = ND >= 2 ? P.p[1][i] : 0.0, z = ND >= 3 ? P.p[2][i] : 0.0;
+            if (!particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz)) continue;
+            const double wj = W ? P.p[3][i] : 1.0;
+            double *g = P.grid + ((int64_t)b[0] * g1 + b[1]) * g2 + b[2];
+#pragma unroll
+            for (int a = 0; a < MA; ++a)
+#pragma unroll
+                for (int c = 0; c < MC; ++c)
+#pragma unroll
+                    for (int d = 0; d < MD; ++d)
+                        red_add(g + (a * g1 + c) * g2 + d, stencil_value<ND, S, W>(wx, wy, wz, a, c, d, wj));
+        }
+    }
+}
+
+template <int ND, int S, bool W>
+static cudaError_t launch_runs_bulk(const DepositParams &P, const TileConfig *gate, int sm_count, cudaStream_t st) {
+    using C = BulkCfg<ND, W>;
+    static bool opted_in[64] = {};                           // per device: > 48 KB of dynamic shared memory
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !opted_in[dev]) {
+        e = cudaFuncSetAttribute(k_deposit_runs_bulk<ND, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) opted_in[dev] = true;
+    }
+    const int64_t want = (P.n / kBulkTile + C::WARPS - 1) / C::WARPS;
+    const int blocks = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);     // one CTA per SM
+    k_deposit_runs_bulk<ND, S, W><<<blocks, C::THREADS, C::SMEM, st>>>(P, gate);
+    return cudaGetLastError();
+}
+
+// the bulk-copy kernel streams plain contiguous arrays only
+template <int ND, int S, bool W>
+static bool bulk_ok(const DepositParams &P) {
+    constexpr int NW = StencilWidth<S>::value;
+    if ((ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW) > 16) return false;      // accumulators + 8 particles in registers
+    static const int forced = [] { const char *e = getenv("PTG_RUNS_IMPL"); return !e ? 0 : e[0] == 'b' ? 1 : 2; }();
+    // measured on cell-ordered cfg2-like input (profiles/r01/ab_runs_bulk_*.log): 2-D TSC weighted 155.6 -> 169.7 Gp/s
+    // (cfg5: 166.0 -> 186.7), 2-D NGP weighted 163.2 -> 247.6 and counting 228.4 -> 367.6 (0.87 of the HBM
+    // roofline); 2-D TSC unweighted is a tie (175 vs 177: arithmetic-bound at 16 B per particle) and keeps
+    // the vector-load kernel, as do the instances not measured yet
+    constexpr bool by_default = S == 0 || (ND == 2 && S == 2 && W);
+    if (forced == 2 || (forced == 0 && !by_default)) return false;
+    if (P.mask != nullptr || P.fuse_kind != 0 || P.n < (int64_t(1) << 13)) return false;
+    for (int k = 0; k < 4; ++k) {
+        const bool used = k < ND || (k == 3 && W);
+        if (used && (P.stride[k] != 1 || (reinterpret_cast<uintptr_t>(P.p[k]) & 15u))) return false;
+    }
+    return true;
 }
 
 // widened windows are compiled where they fit the register file: (S+2)^ndim <= 27 accumulators
@@ -259,6 +493,7 @@ static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, b
         }
         return cudaGetLastError();      // (no widened instance for this stencil: nothing launched)
     }
+    if (bulk_ok<ND, S, W>(P)) return launch_runs_bulk<ND, S, W>(P, gate, sm_count, st);
     if (W && P.fuse_kind) {
         if (vec) k_deposit_runs<ND, S, W, true, 0, W><<<blocks, kRT, 0, st>>>(P, gate);
         else k_deposit_runs<ND, S, W, false, 0, W><<<blocks, kRT, 0, st>>>(P, gate);

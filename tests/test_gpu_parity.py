@@ -595,3 +595,59 @@ def test_masked_deposit_equals_compressed_copy(method):
     got, _ = device.deposit([x, y], w, method=method, mask=torch.ones(n, dtype=torch.bool, device='cuda'), **kw)
     ref, _ = device.deposit([x, y], w, method='global', **kw)
     assert float((got - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
+
+
+_BULK_SCRIPT = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1])
+from oracle import ptg_oracle as oracle
+from postpic_b200 import device
+rng = np.random.default_rng(77)
+bad = []
+for nd in (1, 2, 3):
+    bins = {1: (300,), 2: (40, 30), 3: (12, 10, 8)}[nd]
+    rngs = [(0.0, 1.0), (-1.0, 1.0), (0.0, 2.0)][:nd]
+    for shape in (0, 1, 2, 3):
+        for weighted in (False, True):
+            for order in ('random', 'sorted'):
+                n = 20000 + 13                                   # whole tiles of 256 plus a ragged tail
+                cols = [rng.uniform(lo - 0.05 * (hi - lo), hi + 0.05 * (hi - lo), n) for lo, hi in rngs]
+                if order == 'sorted':                            # long runs: the kernel's fast case
+                    key = np.zeros(n, dtype=np.int64)
+                    for c, (lo, hi), b in zip(cols, rngs, bins):
+                        key = key * (b + 8) + np.floor((c - lo) / (hi - lo) * b).astype(np.int64) + 4
+                    perm = np.argsort(key, kind='stable')
+                    cols = [c[perm] for c in cols]
+                w = rng.uniform(0.1, 1.0, n) if weighted else None
+                fn = {1: oracle.histogram, 2: oracle.histogram2d, 3: oracle.histogram3d}[nd]
+                if nd == 1:
+                    want = fn(cols[0], range=rngs[0], bins=bins[0], weights=w, shape=shape)[0].base
+                else:
+                    want = fn(*cols, weights=w, range=rngs, bins=bins, shape=shape)[0].base
+                t = [torch.from_numpy(c).cuda() for c in cols]
+                tw = torch.from_numpy(w).cuda() if weighted else None
+                grid, plan = device.deposit(t, tw, range=rngs if nd > 1 else rngs[0], bins=bins if nd > 1 else bins[0],
+                                            shape=shape, method='runs')
+                got = grid.cpu().numpy()
+                want = want if want is not None else np.zeros_like(got)
+                tol = 1e-12 * max(np.max(np.abs(want)), 1e-300)
+                if got.shape != want.shape or np.max(np.abs(got - want)) > tol:
+                    bad.append((nd, shape, weighted, order, float(np.max(np.abs(got - want)))))
+print('BAD', bad)
+sys.exit(1 if bad else 0)
+'''
+
+
+@pytest.mark.gpu
+def test_bulk_copy_runs_kernel_every_instance_against_the_oracle():
+    """k_deposit_runs_bulk (cp.async.bulk + mbarrier ring) is the default only where it was measured
+    faster; PTG_RUNS_IMPL=b forces it wherever it exists.  Every (ndim, shape, weighted) instance, random
+    and cell-ordered input, whole tiles plus a ragged tail, against the oracle -- in a child process because
+    the knob is read once per process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PTG_RUNS_IMPL='b')
+    r = subprocess.run([sys.executable, '-c', _BULK_SCRIPT, root], env=env, capture_output=True, text=True, timeout=280)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
