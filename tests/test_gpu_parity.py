@@ -28,9 +28,12 @@ def _skip_unavailable(method, nd, shape):
         pytest.skip("no runs_wide instance for ndim=%d shape=%d" % (nd, shape))
 
 
-@pytest.fixture(scope="module")
+@pytest.fixture
 def ptg():
+    """The drop-in module with its default method; tests that force a method set `ptg.method` themselves
+    and never leak it into the next test."""
     from postpic_b200.particles import _particlestogrid
+    _particlestogrid.method = None
     yield _particlestogrid
     _particlestogrid.method = None
 
@@ -181,14 +184,18 @@ def test_ragged_sizes_around_warp_and_chunk_boundaries(ptg, oracle):
 
 
 def test_multi_chunk_host_pipeline(ptg, oracle):
-    # > 2 pipeline chunks (chunk = 2^22 particles) with a ragged tail
+    # > 2 pipeline chunks (chunk = 2^22 particles) with a ragged tail, through the default method and
+    # through the run-length kernels (unordered input: every particle closes a run)
     n = (1 << 23) + 12345
     rng = np.random.default_rng(12)
     x, y, w = rng.uniform(-0.01, 1.01, n), rng.uniform(-0.01, 1.01, n), rng.uniform(0, 1, n)
-    hg = ptg.histogram2d(x, y, weights=w, range=((0, 1), (0, 1)), bins=(128, 96), shape=2)[0]
     ho = oracle.histogram2d(x, y, weights=w, range=((0, 1), (0, 1)), bins=(128, 96), shape=2)[0]
     _, asum = oracle.accepted_weight([x, y], w, [(0, 1), (0, 1)], [128, 96], 2)
-    assert_parity(hg, ho, asum)
+    for method in (None, 'runs', 'runs_wide'):
+        ptg.method = method
+        hg = ptg.histogram2d(x, y, weights=w, range=((0, 1), (0, 1)), bins=(128, 96), shape=2)[0]
+        assert_parity(hg, ho, asum)
+    ptg.method = None
     # shape 0, unweighted, same size: bit exact
     hg = ptg.histogram2d(x, y, range=((0, 1), (0, 1)), bins=(128, 96), shape=0)[0]
     ho = oracle.histogram2d(x, y, range=((0, 1), (0, 1)), bins=(128, 96), shape=0)[0]
