@@ -272,7 +272,7 @@ template <int ND, bool W> struct BulkCfg {
     static constexpr int FIT = (200 * 1024) / (STAGES * TILE_BYTES) / 4 * 4;
     static constexpr int WARPS = FIT >= PTG_BULK_WARPS ? PTG_BULK_WARPS : FIT;
     static constexpr int THREADS = WARPS * 32;
-    static constexpr size_t SMEM = (size_t)WARPS * STAGES * (TILE_BYTES + 8);
+    static constexpr size_t SMEM = (size_t)WARPS * STAGES * (TILE_BYTES + 16) + WARPS * 128;   // + full / empty barriers, + one word per lane
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -290,6 +290,9 @@ __device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned b
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
     const uint32_t a = smem_u32(bar);
@@ -311,12 +314,16 @@ __global__ void __launch_bounds__(BulkCfg<ND, W>::THREADS, 1) k_deposit_runs_bul
     extern __shared__ __align__(128) unsigned char bulk_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *const ring = reinterpret_cast<double *>(bulk_smem) + (size_t)warp * STAGES * NA * kBulkTile;
-    uint64_t *const bars = reinterpret_cast<uint64_t *>(bulk_smem + (size_t)C::WARPS * STAGES * C::TILE_BYTES) + warp * STAGES;
+    // per warp and stage: `bars` = "tile has landed" (1 arrival + the copy's bytes), `empty` = "every lane
+    // has its copy of the tile" (32 arrivals)
+    uint64_t *const bars = reinterpret_cast<uint64_t *>(bulk_smem + (size_t)C::WARPS * STAGES * C::TILE_BYTES) + warp * 2 * STAGES;
+    uint64_t *const empty = bars + STAGES;
+    unsigned *const sink = reinterpret_cast<unsigned *>(bulk_smem + (size_t)C::WARPS * STAGES * (C::TILE_BYTES + 16)) + threadIdx.x;
     const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
 
     if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < STAGES; ++s) mbar_init(bars + s, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bars + s, 1); mbar_init(empty + s, 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -370,8 +377,27 @@ __global__ void __launch_bounds__(BulkCfg<ND, W>::THREADS, 1) k_deposit_runs_bul
                 v[a][2 * q] = two.x;
                 v[a][2 * q + 1] = two.y;
             }
-        __syncwarp();                                        // every lane has its copy: the slot is free again
-        if (lane == 0 && t + STAGES * t_step < t_end) issue(t + STAGES * t_step, s);
+        // Hand the slot back.  The copy engine may overwrite it only after every lane's shared loads have
+        // RETURNED, not merely issued: behind a queue of reductions that wait on L2 a load can sit in the
+        // memory pipeline for microseconds, longer than the next bulk copy takes to land (seen as particles
+        // whose x, y and weight came from different tiles; profiles/r01/bulk_runs_diag_before_fix.log).
+        // (1) a word computed from one register of each load is stored to shared memory in front of the
+        // arrive (a store cannot be optimised away, and it cannot issue before the loads have delivered);
+        // (2) the arrive is a release on the slot's `empty` barrier, and lane 0 refills the slot only after
+        // all 32 arrivals.
+        {
+            unsigned chk = 0;
+#pragma unroll
+            for (int a = 0; a < NA; ++a)
+#pragma unroll
+                for (int q = 0; q < kBulkPer / 2; ++q) chk ^= (unsigned)__double2hiint(v[a][2 * q]);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_u32(sink)), "r"(chk) : "memory");
+        }
+        mbar_arrive(empty + s);
+        if (lane == 0 && t + STAGES * t_step < t_end) {
+            mbar_wait(empty + s, (unsigned)((k / STAGES) & 1));
+            issue(t + STAGES * t_step, s);
+        }
 
         int cur = -1;
         double acc[MV];

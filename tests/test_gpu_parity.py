@@ -640,6 +640,14 @@ for nd in (1, 2, 3):
                 tol = 1e-12 * max(np.max(np.abs(want)), 1e-300)
                 if got.shape != want.shape or np.max(np.abs(got - want)) > tol:
                     bad.append((nd, shape, weighted, order, float(np.max(np.abs(got - want)))))
+# several tiles per warp of unordered particles on a grid larger than L2: the case in which a refill of a
+# shared-memory slot once overtook the loads that were still reading it (particles with x, y and weight
+# from different tiles).  Index-coded cells: every particle must be found exactly once in its own cell.
+sys.path.insert(0, sys.argv[1] + '/profiles/diag')
+import bulk_runs_diag
+nbad = bulk_runs_diag.run(1 << 21, 1)
+if nbad:
+    bad.append(('index-coded multi-tile', nbad))
 print('BAD', bad)
 sys.exit(1 if bad else 0)
 '''
