@@ -202,6 +202,42 @@ def test_multispecies_dispatch_on_cpu_stack(cpu_stack, monkeypatch, oracle):
     assert h.shape == (4,) and not h.any()
 
 
+def test_field_container_contract():
+    """`Field(matrix, xedges=..., ...)` (datahandling.py:561-612): one edge array per dimension, host matrix
+    kept as numpy; the lazily materialised device grid of SURVEY section 8 row f4 behaves like a host one."""
+    from postpic_b200.particles.particles import Field, _DeviceGrid
+    m = np.arange(12.0).reshape(3, 4)
+    f = Field(m, xedges=np.linspace(0, 1, 4), yedges=np.linspace(-1, 1, 5))
+    assert f.shape == (3, 4) and f.dimensions == 2 and f.device_matrix is None
+    assert f.extent == [0.0, 1.0, -1.0, 1.0] and np.allclose(f.axes[1].grid, [-0.75, -0.25, 0.25, 0.75])
+    assert np.asarray(f) is f.matrix
+    with pytest.raises(ValueError):
+        Field(m, xedges=np.linspace(0, 1, 4))
+
+    class FakeTensor(object):                      # stands in for a CUDA tensor: slicing and a host copy
+        def __init__(self, a):
+            self.a, self.copies = a, 0
+            self.shape = a.shape
+
+        def __getitem__(self, idx):
+            return FakeTensor(self.a[idx])
+
+        def cpu(self):
+            self.copies += 1
+            return self
+
+        def numpy(self):
+            return self.a
+
+    padded = FakeTensor(np.pad(m, 2))
+    g = Field(_DeviceGrid(padded, (slice(2, 5), slice(2, 6))), xedges=np.linspace(0, 1, 4), yedges=np.linspace(-1, 1, 5))
+    assert g.shape == (3, 4) and g.dimensions == 2 and padded.copies == 0          # nothing copied yet
+    assert np.array_equal(g.matrix, m) and padded.copies == 1
+    assert np.array_equal(np.asarray(g), m) and padded.copies == 1                   # cached
+    g.matrix = 2 * m                                                                 # h-like in-place users replace it
+    assert g.device_matrix is None and np.array_equal(g.matrix, 2 * m)
+
+
 def test_dummy_species_follows_the_reference_recipe():
     # datareader/dummy.py:43-61 restated: seeded, independent of the caller's RNG state
     from postpic_b200 import ArraySource
