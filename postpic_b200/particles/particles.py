@@ -423,8 +423,10 @@ class MultiSpecies(object):
         if simgrid:
             simextent = True
         on_device = bool(self._sources) and all(s.device is not None for s in self._sources)
+        on_host = bool(self._sources) and all(s.device is None for s in self._sources)
+        several = sum(1 for s in self._sources if len(s) > 0) > 1
         try:
-            if on_device and self.npart > 0:
+            if (on_device or (on_host and several)) and self.npart > 0:
                 data = None                       # evaluated per species below, nothing is concatenated
                 for sp in sps:                    # (unknown scalars must still raise here)
                     MultiSpecies(self._sources[0])(sp)
@@ -451,10 +453,49 @@ class MultiSpecies(object):
             edges = [edges_of(r, bins[i]) for i, r in zip(range(h.ndim), ranges)]
             return h, edges
 
-        if data is None:
+        if data is None and on_device:
             return self._createHistgram_per_species(sps, ranges, weights, bins, shape, keep_on_device)
+        if data is None:
+            return self._createHistgram_host_per_species(sps, ranges, weights, bins, shape)
         w = self._weights(weights)
         h, edges = histogramdd(data, weights=w, range=ranges, bins=bins, shape=shape)
+        dV = np.prod([edge[1] - edge[0] for edge in edges])
+        h /= dV
+        return h, edges
+
+    def _createHistgram_host_per_species(self, sps, ranges, weights, bins, shape):
+        """Several host-resident species: one deposit per species, summed in the ghost-padded accumulator of
+        the first -- deposition is linear in the particle set -- instead of `np.hstack`-ing every axis and
+        weight array of all species first (particles.py:662-674).  Range ends that are not given are the
+        minimum / maximum over all species, as they would be for the concatenated arrays."""
+        from ._routines import _minmax
+        nd = len(sps)
+        per = []
+        for src in self._sources:
+            m = MultiSpecies(src)
+            m._filters = list(self._filters)
+            d = [np.asarray(m(sp), dtype='float64') for sp in sps]
+            if len(d[0]) == 0:
+                continue
+            per.append((d, np.asarray(m._weights(weights), dtype='float64')))
+        rng = []
+        cache = {}
+        for a in range(nd):
+            r = ranges[a]
+            lo, hi = (None, None) if r is None else (r[0], r[1])
+            if lo is None or hi is None:
+                mm = np.array([_minmax(d[a], cache) for d, _ in per])       # np.min / np.max propagate NaN
+                lo = np.min(mm[:, 0]) if lo is None else lo
+                hi = np.max(mm[:, 1]) if hi is None else hi
+            rng.append((lo, hi))
+        h = edges = None
+        for d, w in per:
+            hk, ek = histogramdd(d, weights=w, range=rng, bins=bins, shape=shape)
+            if h is None:
+                h, edges = hk, ek
+            else:
+                acc = h.base if h.base is not None else h
+                acc += hk.base if hk.base is not None else hk
         dV = np.prod([edge[1] - edge[0] for edge in edges])
         h /= dV
         return h, edges

@@ -169,6 +169,26 @@ def test_multispecies_dispatch_on_cpu_stack(cpu_stack, monkeypatch, oracle):
     f1 = p.createField('x', 'y', bins=[50, 40], simextent=True)
     f2 = (p + p).createField('x', 'y', bins=[50, 40], simextent=True)
     assert np.allclose(2 * f1.matrix, f2.matrix)                    # test/test_particles.py:37-49
+    # several host species are deposited one by one into one accumulator instead of being concatenated:
+    # same result as the deposit of the concatenated arrays, ghost cells included, with and without ranges
+    other = P.ArraySource('ion', dict(x=rng.normal(1, 2, 3000), y=rng.normal(0, 1, 3000), z=np.zeros(3000),
+                                      px=np.zeros(3000), py=np.zeros(3000), pz=np.zeros(3000), weight=0.5,
+                                      mass=1836 * me))
+    both = P.MultiSpecies(src, other)
+    xs = np.hstack([src.atomic('x'), other.atomic('x')])
+    ys = np.hstack([src.atomic('y'), other.atomic('y')])
+    ws = np.hstack([np.full(n, 2.0), np.full(3000, 0.5)])
+    for kw, rngs in ((dict(rangex=(-4, 4), rangey=(-3, 3)), ((-4, 4), (-3, 3))),
+                     (dict(), ((xs.min(), xs.max()), (ys.min(), ys.max())))):
+        hb, eb = both._createHistgram('x', 'y', bins=[30, 20], shape=3, **kw)
+        hc, ex, ey = oracle.histogram2d(xs, ys, weights=ws, range=rngs, bins=(30, 20), shape=3)
+        assert np.allclose(hb, hc / ((ex[1] - ex[0]) * (ey[1] - ey[0])), rtol=1e-12, atol=1e-300)
+        assert hb.base is not None and hb.base.shape == hc.base.shape
+        assert np.array_equal(eb[0], ex) and np.array_equal(eb[1], ey)
+    fb = both.filter('x > 0').createField('x', bins=[16], rangex=(-4, 4), shape=1)
+    keep = xs > 0
+    h1, e1 = oracle.histogram(xs[keep], weights=ws[keep], range=(-4, 4), bins=16, shape=1)
+    assert np.allclose(fb.matrix, h1 / (e1[1] - e1[0]), rtol=1e-12) and fb.infostring == '%d npart in 2 species' % keep.sum()
     # 1/dV normalisation, weight * (expr), default shape 2
     h, ex, ey = oracle.histogram2d(src.atomic('x'), src.atomic('y'), weights=np.full(n, 2.0),
                                    range=((-4, 4), (-4, 4)), bins=(50, 40), shape=2)
