@@ -1,0 +1,68 @@
+"""`MultiSpecies._createHistgram` / `createField` against golden vectors
+produced by the REAL postpic run in the build container (tests/golden/make_createfield_golden.py:
+its own createField, histogramdd, scalar expressions and compiled _particlestogrid on its own dummy reader).
+
+  * CPU (`not gpu`): this package's host stack with the oracle in place of the CUDA module -- checks the host
+    logic (scalar evaluation, weights, ranges, filters, species concatenation, 1/dV, names/units) bit-tightly;
+  * GPU: the same calls through the CUDA library, host-resident and device-resident species.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_createfield_golden import CASES, NPART          # noqa: E402  (case table only; no postpic import)
+
+GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "createfield_golden.npz"))
+
+
+def _collection(dims, cond, doubled, device=None):
+    from postpic_b200 import MultiSpecies, ArraySource
+    ms = MultiSpecies(ArraySource.dummy(NPART, dimensions=dims, device=device))
+    if doubled:
+        ms = ms + ms            # (the shim adds before filtering; no case does both)
+    if cond is not None:
+        ms = ms.filter(cond)
+    return ms
+
+
+def _check(key, f, ms, rtol):
+    ref = GOLDEN[key + "_matrix"]
+    assert f.matrix.shape == ref.shape
+    assert np.max(np.abs(f.matrix - ref)) <= rtol * np.max(np.abs(ref))
+    for a, ax in enumerate(f.axes):
+        assert np.allclose(ax.grid_node, GOLDEN[key + "_edges%d" % a], rtol=1e-15, atol=0)
+        assert ax.name == str(GOLDEN[key + "_axname%d" % a])
+        assert ax.unit == str(GOLDEN[key + "_axunit%d" % a])
+    assert f.name == str(GOLDEN[key + "_name"])
+    assert f.infostring == str(GOLDEN[key + "_infostring"])
+    assert len(ms) == int(GOLDEN[key + "_npart"])
+
+
+@pytest.fixture
+def cpu_stack(monkeypatch, oracle):
+    from postpic_b200.particles import _routines
+    import postpic_b200.particles.particles as P
+    monkeypatch.setattr(_routines, "ptg", oracle)
+    monkeypatch.setattr(P, "histogramdd", _routines.histogramdd)
+    return _routines
+
+
+@pytest.mark.parametrize("key,dims,sps,kw,cond,doubled", CASES, ids=[c[0] for c in CASES])
+def test_createfield_matches_real_postpic_on_cpu_stack(cpu_stack, key, dims, sps, kw, cond, doubled):
+    ms = _collection(dims, cond, doubled)
+    f = ms.createField(*sps, **{k: (list(v) if isinstance(v, list) else v) for k, v in kw.items()})
+    _check(key, f, ms, rtol=1e-13)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("resident", ["host", "device"])
+@pytest.mark.parametrize("key,dims,sps,kw,cond,doubled", CASES, ids=[c[0] for c in CASES])
+def test_createfield_matches_real_postpic_on_gpu(key, dims, sps, kw, cond, doubled, resident):
+    from postpic_b200.particles import _particlestogrid
+    _particlestogrid.method = None
+    ms = _collection(dims, cond, doubled, device=("cuda:0" if resident == "device" else None))
+    f = ms.createField(*sps, **{k: (list(v) if isinstance(v, list) else v) for k, v in kw.items()})
+    _check(key, f, ms, rtol=1e-11)
