@@ -66,3 +66,43 @@ def test_createfield_matches_real_postpic_on_gpu(key, dims, sps, kw, cond, doubl
     ms = _collection(dims, cond, doubled, device=("cuda:0" if resident == "device" else None))
     f = ms.createField(*sps, **{k: (list(v) if isinstance(v, list) else v) for k, v in kw.items()})
     _check(key, f, ms, rtol=1e-11)
+
+
+# ---- row a5: the call forms of histogramdd against the real postpic's histogramdd ----
+from make_createfield_golden import hdd_inputs          # noqa: E402
+
+HDD_KEYS = sorted(hdd_inputs().keys())
+
+
+def _check_hdd(key, h, edges, rtol, exact_counts):
+    ref = GOLDEN["hdd_" + key + "_h"]
+    assert h.shape == ref.shape and h.dtype == np.float64
+    if exact_counts:
+        assert np.array_equal(h, ref)
+    else:
+        assert np.max(np.abs(h - ref)) <= rtol * np.max(np.abs(ref))
+    for a, e in enumerate(edges):
+        assert np.array_equal(e, GOLDEN["hdd_" + key + "_edges%d" % a])
+
+
+def _is_count(key):
+    kw = hdd_inputs()[key][1]
+    return kw.get('shape', 2) == 0 and 'weights' not in kw
+
+
+@pytest.mark.parametrize("key", HDD_KEYS)
+def test_histogramdd_matches_real_postpic_on_cpu_stack(cpu_stack, key):
+    data, kw = hdd_inputs()[key]
+    h, edges = cpu_stack.histogramdd(data, **kw)
+    _check_hdd(key, h, edges, 1e-14, _is_count(key))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", HDD_KEYS)
+def test_histogramdd_matches_real_postpic_on_gpu(key):
+    from postpic_b200 import histogramdd
+    from postpic_b200.particles import _particlestogrid
+    _particlestogrid.method = None
+    data, kw = hdd_inputs()[key]
+    h, edges = histogramdd(data, **kw)
+    _check_hdd(key, h, edges, 1e-12, _is_count(key))
