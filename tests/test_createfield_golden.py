@@ -106,3 +106,34 @@ def test_histogramdd_matches_real_postpic_on_gpu(key):
     data, kw = hdd_inputs()[key]
     h, edges = histogramdd(data, **kw)
     _check_hdd(key, h, edges, 1e-12, _is_count(key))
+
+
+# ---- the kinetic scalars of scalarproperties.py:183-205, evaluated by the reference's own expressions ----
+from make_createfield_golden import SCALAR_KINDS, SCALAR_N          # noqa: E402
+
+
+@pytest.mark.parametrize("kind", SCALAR_KINDS)
+def test_scalar_expressions_match_real_postpic(kind):
+    from postpic_b200 import MultiSpecies, ArraySource
+    ms = MultiSpecies(ArraySource.dummy(SCALAR_N, dimensions=2))
+    ref = GOLDEN["scalar_" + kind]
+    got = np.asarray(ms(kind), dtype=np.float64)
+    assert got.shape == ref.shape
+    assert np.max(np.abs(got - ref)) <= 4e-16 * np.max(np.abs(ref))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", [k for k in SCALAR_KINDS if k not in ('beta', 'v')])
+def test_fused_kinetic_weights_match_real_postpic(kind):
+    """ptg_weights_f64 (the one-pass CUDA evaluation that createField fuses into the deposit) against the
+    values the reference's scalar-property expressions give; 1e-14 relative (same operations, same order)."""
+    import torch
+    from postpic_b200 import ArraySource, device
+    src = ArraySource.dummy(SCALAR_N, dimensions=2)
+    a = src._arrays
+    px, py, pz = (torch.from_numpy(np.ascontiguousarray(a[k])).cuda() for k in ('px', 'py', 'pz'))
+    import scipy.constants as sc                     # the reference's scalar context takes c and e from scipy
+    out = device.kinetic_weights(kind, px, py, pz, None, mass=float(a['mass']), c=sc.c,
+                                 elementary_charge=sc.elementary_charge)
+    ref = GOLDEN["scalar_" + kind]
+    assert np.max(np.abs(out.cpu().numpy() - ref)) <= 1e-14 * np.max(np.abs(ref))
