@@ -57,8 +57,14 @@ _SCALARS = {
     'Ekin': ('gamma_m1 * mass * c**2', 'J'),
     'Ekin_MeV': ('Ekin / elementary_charge / 1e6', 'MeV'),
     'Ekin_MeV_amu': ('Ekin / elementary_charge / 1e6 / mass_u', 'MeV/u'),
-    'Ekin_keV': ('Ekin / elementary_charge / 1e3', 'keV'),
+    'Ekin_MeV_qm': ('Ekin / elementary_charge / 1e6 / mass_u * charge_e', 'MeV * q/m'),
+    'Ekin_keV': ('Ekin / elementary_charge / 1e3', 'keV/u'),          # sic: the reference's unit string (:205)
     'Ekin_keV_amu': ('Ekin / elementary_charge / 1e3 / mass_u', 'keV/u'),
+    'Ekin_keV_qm': ('Ekin / elementary_charge / 1e3 / mass_u * charge_e', 'keV * q/m'),
+    'angle_xaxis': ('arctan2(sqrt(py**2 + pz**2), px)', 'rad'),
+    'angle_yaxis': ('arctan2(sqrt(pz**2 + px**2), py)', 'rad'),
+    'angle_zaxis': ('arctan2(sqrt(px**2 + py**2), pz)', 'rad'),
+    't': ('time', 's'),
     'angle_xy': ('arctan2(py, px)', 'rad'), 'angle_yx': ('arctan2(px, py)', 'rad'),
     'angle_yz': ('arctan2(pz, py)', 'rad'), 'angle_zy': ('arctan2(py, pz)', 'rad'),
     'angle_zx': ('arctan2(px, pz)', 'rad'), 'angle_xz': ('arctan2(pz, px)', 'rad'),
@@ -69,12 +75,25 @@ _ATOMIC_UNITS = {'x': 'm', 'y': 'm', 'z': 'm', 'px': 'kg*m/s', 'py': 'kg*m/s', '
                  'weight': 'npartpermacro', 'mass': 'kg', 'charge': 'C', 'id': '', 'time': 's'}
 
 
+# short symbols whose ScalarProperty carries the long name (scalarproperties.py:161-170)
+_SYMBOL_NAMES = {'w': 'weight', 'm': 'mass', 'q': 'charge', 'm_u': 'mass_u', 'q_e': 'charge_e', 't': 'time'}
+
+
 def _unit_of(expr):
     if expr in _ATOMIC_UNITS:
         return _ATOMIC_UNITS[expr]
     if expr in _SCALARS:
         return _SCALARS[expr][1]
     return ''
+
+
+def _findscalarattr(scalarf, attrib, default='unknown'):
+    """`name` / `unit` of a scalar given as an object with that attribute or as the name of a known
+    scalar; anything else -- e.g. an expression string -- is 'unknown' (particles.py:44-57)."""
+    ret = getattr(scalarf, attrib, None) if not isinstance(scalarf, str) else None
+    if isinstance(scalarf, str) and (scalarf in _SCALARS or scalarf in _ATOMIC_UNITS):
+        ret = _SYMBOL_NAMES.get(scalarf, scalarf) if attrib == 'name' else _unit_of(scalarf)
+    return default if ret is None else ret
 
 
 class ArraySource(object):
@@ -132,7 +151,7 @@ class ArraySource(object):
         if device is not None:
             idx = _device._torch().device(device).index
             arrs = {k: _device.upload(v, idx) for k, v in arrs.items()}
-        arrs.update(weight=1.0, mass=me, charge=-qe)
+        arrs.update(weight=1.0, mass=me, charge=-qe, time=n * 1e-10)      # dummy.py:77-81: time = timestep * 1e-10
         extent = {'x': (-2.0, 10.0), 'y': (-5.0, 5.0), 'z': (-4.0, 4.0)}
         return cls('electron', arrs, extent={k: extent[k] for k in 'xyz'[:dimensions]})
 
@@ -352,8 +371,8 @@ class MultiSpecies(object):
             ns = _Namespace(s, funcs)
             try:
                 val = eval(str(expr), {'__builtins__': {}}, ns)          # noqa: S307
-            except NameError as exc:        # unknown scalar: the reference raises KeyError here
-                raise KeyError(str(exc))
+            except NameError as exc:        # unknown scalar: the reference raises KeyError('"name" not found!')
+                raise KeyError('"{}" not found!'.format(getattr(exc, 'name', None) or str(exc)))
             if np.ndim(val) == 0 and not _device.is_cuda_tensor(val):
                 val = s.atomic('weight') * 0 + float(val) if 'weight' in s._arrays else np.full(len(s), float(val))
             if self._filters and not getattr(self, '_raw', False):
@@ -579,15 +598,13 @@ class MultiSpecies(object):
         edgekw = {k: e for k, e in zip(['xedges', 'yedges', 'zedges'], edges)}
         ret = Field(h, **edgekw)
         if 'weights' in kwargs:
-            name = getattr(kwargs['weights'], 'name', kwargs['weights'])
-            name = name if isinstance(name, str) else 'distfn'
+            name = _findscalarattr(kwargs['weights'], 'name')
         ret.name = str(name) + self.species
         ret.label = self.species
         ret.name = title if title else ret.name
         for i, sp in enumerate(sps):
-            sym = getattr(sp, 'symbol', sp)
-            ret.axes[i].unit = getattr(sp, 'unit', _unit_of(sym))
-            ret.axes[i].name = getattr(sp, 'name', sym if isinstance(sym, str) else '')
+            ret.axes[i].unit = _findscalarattr(sp, 'unit')
+            ret.axes[i].name = _findscalarattr(sp, 'name')
         ret.infostring = '{:.0f} npart in {:.0f} species'.format(self.npart, self.nspecies)
         ret.infos = self.getcompresslog()['all']
         return ret

@@ -137,3 +137,37 @@ def test_fused_kinetic_weights_match_real_postpic(kind):
                                  elementary_charge=sc.elementary_charge)
     ref = GOLDEN["scalar_" + kind]
     assert np.max(np.abs(out.cpu().numpy() - ref)) <= 1e-14 * np.max(np.abs(ref))
+
+
+def test_whole_scalar_context_matches_real_postpic():
+    """Every scalar of the reference's default context (scalarproperties.py:159-222): same name, same unit,
+    same per-particle value on the dummy species (the ones the 2-D dummy reader cannot provide raise KeyError
+    in both)."""
+    from postpic_b200 import MultiSpecies, ArraySource
+    from postpic_b200.particles.particles import _findscalarattr
+    ms = MultiSpecies(ArraySource.dummy(SCALAR_N, dimensions=2))
+    table = GOLDEN["ctx_table"]
+    assert len(table) == 56
+    for key, name, unit, available in table:
+        assert _findscalarattr(str(key), 'name') == str(name), key
+        assert _findscalarattr(str(key), 'unit') == str(unit), key
+        if available == '1':
+            ref = GOLDEN["ctx_" + str(key)]
+            got = np.asarray(ms(str(key)), dtype=np.float64)
+            scale = np.max(np.abs(ref))
+            assert got.shape == ref.shape and np.max(np.abs(got - ref)) <= 1e-15 * scale + 0.0, key
+        else:
+            with pytest.raises(KeyError):
+                ms(str(key))
+
+
+def test_field_and_axis_naming_rules(cpu_stack):
+    """Expression strings are 'unknown' (name and unit), aliases carry the long name (particles.py:44-57)."""
+    from postpic_b200 import MultiSpecies, ArraySource
+    ms = MultiSpecies(ArraySource.dummy(SCALAR_N, dimensions=2))
+    f = ms.createField('x_um', 'q_e', bins=[4, 4], weights='gamma*2', rangex=(-3e6, 3e6), rangey=(-2, 0))
+    assert [f.name, f.axes[0].name, f.axes[0].unit, f.axes[1].name, f.axes[1].unit] == [str(v) for v in GOLDEN["naming"]]
+    f = ms.createField('px*2', bins=[4], rangex=(0, 1e-21))
+    assert [f.name, f.axes[0].name, f.axes[0].unit] == [str(v) for v in GOLDEN["naming_expr_axis"]]
+    with pytest.raises(KeyError, match='"zzz" not found!'):
+        ms.createField('x', 'zzz', bins=[4, 4])
