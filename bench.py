@@ -79,16 +79,19 @@ def make_cloud_device(name, n, seed, order, device):
     nd, shape, _, bins, ranges, _ = WORKLOADS[name]
     g = torch.Generator(device=device).manual_seed(seed)
     coords = []
+    pick = None
+    if name == "cfg5":
+        # 90 % of the PARTICLES in the patch [0.45, 0.55)^2 = 1 % of the cells, 10 % uniform over the box
+        # (SURVEY.md section 8d): one draw per particle, shared by both axes
+        pick = torch.rand(n, dtype=torch.float32, device=device, generator=g) < 0.9
     for a in range(nd):
         lo, hi = ranges[a]
         u = torch.rand(n, dtype=torch.float64, device=device, generator=g)
-        if name == "cfg5":
-            # 90 % of the particles in the patch [0.45, 0.55)^2 = 1 % of the cells
-            pick = torch.rand(n, dtype=torch.float32, device=device, generator=g) < 0.9
+        if pick is not None:
             u = torch.where(pick, 0.45 + 0.1 * u, u)
-            del pick
         coords.append(lo + (hi - lo) * u)
         del u
+    del pick
     if name == "cfg4":
         # Ekin_MeV-like weights of a thermal electron species (p ~ N(0, 0.1 me c) per axis)
         p2 = sum((0.1 * torch.randn(n, dtype=torch.float64, device=device, generator=g)) ** 2 for _ in range(3))
@@ -121,11 +124,11 @@ def make_cloud_host(name, n, seed):
     nd, shape, _, bins, ranges, _ = WORKLOADS[name]
     rng = np.random.default_rng(seed)
     coords = []
+    pick = rng.random(n) < 0.9 if name == "cfg5" else None
     for a in range(nd):
         lo, hi = ranges[a]
         u = rng.random(n)
-        if name == "cfg5":
-            pick = rng.random(n) < 0.9
+        if pick is not None:
             u = np.where(pick, 0.45 + 0.1 * u, u)
         coords.append(lo + (hi - lo) * u)
     if name == "cfg4":

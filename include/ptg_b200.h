@@ -72,6 +72,13 @@ extern "C" {
                                        runs alive when neighbours' base cells differ by one (odd
                                        shapes on cell-ordered input); (S+2)^ndim <= 27 only        */
 
+/* Shared-memory tiles (method TILED, also when AUTO picks it) accumulate in 64-bit fixed point on native
+ * 32-bit shared atomics: each contribution is rounded to a multiple of 2^-45 of the power of two above the
+ * largest sampled |weight| (<= 2^-46 relative rounding per contribution; integer-valued weights below 2^45
+ * stay exact; larger / non-finite weights take the exact path), ~3x the rate of the fp64 CAS loop.  This flag
+ * keeps the tile in fp64 (every contribution added in fp64, as all other methods do).                     */
+#define PTG_EXACT_ACCUM      0x100u
+
 /* ---- introspection ------------------------------------------------------------- */
 int         ptg_abi_version(void);
 const char *ptg_last_error(void);

@@ -236,7 +236,7 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
             int rc = next_tile_config(d, &cfg);
             if (rc) return rc;
             const bool force = method == PTG_METHOD_TILED;
-            PTG_CUDA(ptg::deposit_tiled(ndim, shape, P, cfg, force, d->sm_count, st));
+            PTG_CUDA(ptg::deposit_tiled(ndim, shape, P, cfg, force, (flags & PTG_EXACT_ACCUM) != 0, d->sm_count, st));
             if (!force) {
                 PTG_CUDA(ptg::deposit_runs(ndim, shape, P, cfg, false, d->sm_count, st));
                 if (ptg::runs_wide_available(ndim, shape))

@@ -476,11 +476,11 @@ static bool bulk_ok(const DepositParams &P) {
     static const int forced = [] { const char *e = getenv("PTG_RUNS_IMPL"); return !e ? 0 : e[0] == 'b' ? 1 : 2; }();
     // Measured on cell-ordered cfg2-like input (profiles/r01/ab_runs_bulk_*.log): 2-D TSC weighted 155.6 -> 169.7 Gp/s
     // (cfg5: 166.0 -> 186.7), 2-D NGP weighted 163.2 -> 247.6 and counting 228.4 -> 367.6 (0.87 of the HBM
-    // roofline).  OPT-IN ONLY (PTG_RUNS_IMPL=b) for now: it matches the oracle on every instance when a warp
-    // sees one tile and conserves mass on 1e8 cell-ordered particles, but two suite tests that push several
-    // tiles of UNORDERED particles per warp through it (multi-chunk host pipeline, 40000 x 5000 grid) lost the
-    // weight of a handful of particles -- a hazard in the slot hand-back that is not understood yet.
-    constexpr bool by_default = false;
+    // roofline).  Default since round 2: the slot hand-back hazard of its first version (a refill overtaking shared
+    // loads still queued behind reductions) is closed by the release-arrive on the per-slot `empty` barrier, and
+    // the whole GPU suite incl. the BASELINE-geometry parity tests passes with it forced on every instance
+    // (profiles/r02/suite_runs_bulk.log).  PTG_RUNS_IMPL=v keeps the vector-load kernel (A/B runs).
+    constexpr bool by_default = true;
     if (forced == 2 || (forced == 0 && !by_default)) return false;
     if (P.mask != nullptr || P.fuse_kind != 0 || P.n < (int64_t(1) << 13)) return false;
     for (int k = 0; k < 4; ++k) {

@@ -17,6 +17,22 @@
 // locality (i.i.d. positions over a grid much larger than the tile) the probe marks
 // the tile as useless and the launcher's second kernel (method ROWS) does the work.
 //
+//
+// Accumulation inside the tile (round 2): sm_100a has no native fp64 shared-memory atomic -- atomicAdd(double)
+// is a CAS loop (ATOMS.CAST.SPIN.64) that sustains 48 Gparticles/s for a 2-D TSC stencil -- but it has a
+// native 32-bit integer one (ATOMS.ADD).  The tile therefore holds 64-bit FIXED-POINT sums as two 32-bit
+// words per cell: a contribution v (computed in fp64 exactly as the reference does) is rounded to
+// round(v / q) quanta, the low word is added with a returning atomic whose old value yields the carry, the
+// high word (plus carry) with a second one: 143 Gparticles/s for the same stencil
+// (profiles/r02/microbench5_b200.log).  q = 2^(e-45), 2^e = the power of two above the largest |weight| the
+// probe sampled, so each contribution is rounded by at most 2^-46 of that weight (per bin |error| <=
+// n_bin * q / 2, against the 1e-12 * max|bin| bar: cfg2 2.4e-11 worst case vs 6e-11; integer weights below
+// 2^45 are exact, and integer addition is associative, so the tile sums do not depend on the order of the
+// atomics).  The 64-bit range is guarded, not assumed: every lane tracks the sum of |w| it has put into the
+// tile and the CTA merges the tile into the fp64 grid before 2^63 quanta could be reached in any cell;
+// particles whose |w| exceeds 2^e (rarer than one in the probe's sample size) or is not finite take the exact
+// RED.F64 path.  Flag PTG_EXACT_ACCUM keeps the fp64 CAS tile.
+//
 // Replaces the loops of /root/reference/postpic/particles/_particlestogrid.pyx
 // :70-129 (1-D), :181-276 (2-D), :341-463 (3-D).
 #include "ptg_internal.cuh"
@@ -26,8 +42,26 @@ namespace ptg {
 constexpr int kTT = 512;                  // probe CTA width
 // CTA width of the tiled kernel by stencil size: small stencils need few registers, so more warps
 // can keep shared-memory atomics in flight (one CTA per SM owns the whole 200 KB tile)
-template <int NV> struct TileThreads { static constexpr int value = NV <= 4 ? 1024 : NV <= 9 ? 768 : 512; };
-constexpr int kEvalEvery = 4;             // sub-chunks between hit-rate evaluations
+#ifndef PTG_TILE_THREADS_9
+#define PTG_TILE_THREADS_9 768
+#endif
+template <int NV> struct TileThreads { static constexpr int value = NV <= 4 ? 1024 : NV <= 9 ? PTG_TILE_THREADS_9 : 512; };
+#ifndef PTG_TILE_EVAL
+#define PTG_TILE_EVAL 4
+#endif
+constexpr int kEvalEvery = PTG_TILE_EVAL;  // sub-chunks between hit-rate evaluations
+constexpr int kTV = 4;                    // consecutive particles per lane and sub-chunk (one 256-bit load per array)
+
+// the four consecutive doubles of one lane = one 32-byte sector: LDG.E.NA.EFL2.256, not allocated in L1, evict-first in L2
+__device__ __forceinline__ void tile_ld4(const double *p, double (&v)[4]) {
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.b64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    v[0] = __longlong_as_double((long long)a);
+    v[1] = __longlong_as_double((long long)b);
+    v[2] = __longlong_as_double((long long)c);
+    v[3] = __longlong_as_double((long long)d);
+}
 
 // ---------------------------------------------------------------------------------
 // block-wide sum of a long long (all threads get the result)
@@ -49,6 +83,48 @@ __device__ __forceinline__ long long block_sum(long long v, long long *scratch /
     return scratch[32];
 }
 
+// block-wide maximum of a non-negative double (all threads get the result)
+__device__ __forceinline__ double block_max(double v, long long *scratch /* >= 33 */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = __double_as_longlong(v);
+    __syncthreads();
+    if (warp == 0) {
+        double t = lane < (int)(blockDim.x >> 5) ? __longlong_as_double(scratch[lane]) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+        if (lane == 0) scratch[32] = __double_as_longlong(t);
+    }
+    __syncthreads();
+    return __longlong_as_double(scratch[32]);
+}
+
+// ---- 64-bit fixed-point accumulation on two native 32-bit shared-memory atomics --------------------
+// lo[c] / hi[c] = low / high word of cell c's two's-complement sum of quanta.  The returning add on the low
+// word tells whether it wrapped; the carry rides on the (non-returning) add of the high word.  Additions
+// commute, so any interleaving of the atomics of different threads gives the same 64-bit sum.
+constexpr int kFxHi = kTileCells;         // hi word of cell c lives kFxHi words after its lo word
+__device__ __forceinline__ void fx_add(unsigned *lo, int c, double v, double inv_q) {
+    const long long q = __double2ll_rn(__dmul_rn(v, inv_q));
+    const unsigned l = (unsigned)q, h = (unsigned)((unsigned long long)q >> 32);
+    const unsigned old = atomicAdd(lo + c, l);
+    atomicAdd(lo + kFxHi + c, h + ((old + l) < old ? 1u : 0u));
+}
+__device__ __forceinline__ long long fx_take(unsigned *lo, int c) {         // read and clear
+    const unsigned l = lo[c], h = lo[kFxHi + c];
+    lo[c] = 0u;
+    lo[kFxHi + c] = 0u;
+    return (long long)(((unsigned long long)h << 32) | l);
+}
+// |stencil weight| <= 2 on an axis the reference tests on the truncated int (extrapolated weights of particles
+// just below the range), <= 1 elsewhere; at most two such axes -> |contribution| <= 4 |w|.
+// A cell must stay below 2^63 quanta = 2^(18+e) in units of the weights: the lanes of a CTA of TT threads may
+// put sum|w| < 2^(16+e) into the tile between two merges; a lane asks for a merge once its own share reaches
+// fx_lane_limit(TT, slack) * 2^e, `slack` = particles a lane may add between two checks (each |w| <= 2^e).
+__host__ __device__ constexpr double fx_lane_limit(int tt, int slack) { return 65536.0 / tt - slack; }
+
 // stencil base cell of one particle on every axis (the weights are discarded): used by the probe
 template <int ND, int S>
 __device__ __forceinline__ bool base_cells(const DepositParams &P, double x, double y, double z, int (&b)[3]) {
@@ -60,7 +136,7 @@ __device__ __forceinline__ bool base_cells(const DepositParams &P, double x, dou
 // probe: pick the window shape
 // ---------------------------------------------------------------------------------
 template <int ND, int S>
-__global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig *cfg, int force, int wide_ok) {
+__global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig *cfg, int force, int wide_ok, int exact) {
     __shared__ long long scratch[34];
     __shared__ bool s_last;
     constexpr int NW = StencilWidth<S>::value;
@@ -70,6 +146,7 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
         part.mad[0] = part.mad[1] = part.mad[2] = 0.f;
         part.cnt = part.eq_pairs = part.all_pairs = part.near_pairs = 0;
         part.pad = 0;
+        part.wmax = 0.0;
         if (P.n >= 2 * kTT) {
             const int64_t start = (P.n - kTT) / (kProbeBlocks - 1) * blockIdx.x;
             const int64_t i = start + threadIdx.x;
@@ -78,6 +155,14 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
             const double z = ND >= 3 ? ld_stream(P.p[2] + i * P.stride[2]) : 0.0;
             int b[3];
             const bool ok = base_cells<ND, S>(P, x, y, z, b);
+            // largest finite |weight| of the sample: sets the quantum of the fixed-point tile
+            double aw = 1.0;
+            if (P.p[3] != nullptr || P.fuse_kind != 0) {
+                aw = P.p[3] != nullptr ? fabs(ld_stream(P.p[3] + i * P.stride[3])) : 1.0;
+                if (P.fuse_kind != 0) aw = fabs(__dmul_rn(aw, fused_factor(P, i)));
+                if (!(aw <= 1.79769313486231570e308)) aw = 0.0;
+            }
+            part.wmax = block_max(aw, scratch);
             const long long cnt = block_sum(ok ? 1 : 0, scratch);
             if (cnt >= 32) {
                 part.cnt = (int)cnt;
@@ -116,8 +201,10 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
     double mad_sum[3] = {0, 0, 0};
     int blocks_used = 0;
     long long eq_pairs = 0, all_pairs = 0, near_pairs = 0;
+    double wmax = 0.0;
     for (int blk = 0; blk < (int)gridDim.x; ++blk) {
         const volatile TileConfig::Part *q = &cfg->part[blk];
+        wmax = fmax(wmax, q->wmax);
         if (q->cnt < 32) continue;
         ++blocks_used;
         for (int a = 0; a < ND; ++a) mad_sum[a] += q->mad[a];
@@ -167,19 +254,32 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
         double hit = 1;
         for (int a = 0; a < ND; ++a) hit *= fmin(1.0, (double)c.ext[a] / need[a]);
         c.est_hit = (float)hit;
-        // A band of whole rows (x-ordered input, uniform along the last axis) is no win: its
-        // shared-memory CAS atomics run at about the rate of the L2 reductions of method ROWS
-        // (measured 36 vs 38 Gp/s, 2-D TSC).  The tile pays off when it is a true window on the
-        // last axis (bunches), or when the whole grid fits (1-D and small histograms).
+        // With the fp64 CAS tile (PTG_EXACT_ACCUM) a band of whole rows (x-ordered input, uniform along the
+        // last axis) is no win: the CAS loop runs at about the rate of the L2 reductions of method ROWS
+        // (measured 36 vs 38 Gp/s, 2-D TSC), so the tile is chosen only when it is a true window on the last
+        // axis (bunches) or holds the whole grid (1-D and small histograms).  The fixed-point tile is ~3x
+        // faster than either and takes every input that mostly hits the window.
         bool whole = true;
         for (int a = 0; a < ND; ++a) whole = whole && c.ext[a] >= P.dims[a];
         const bool windowed_last = c.ext[ND - 1] < P.dims[ND - 1];
-        if (force || (hit >= 0.45 && (whole || windowed_last || ND == 1))) c.mode = kModeTiled;
+        const bool fx = !exact && wmax > 0.0;
+        if (force || (hit >= 0.45 && (whole || windowed_last || ND == 1 || fx))) c.mode = kModeTiled;
     }
     // long runs of equal base cells: register run-length accumulation beats the tile
     // (break-even is an average run of ~2.5 particles)
     if (!force && c.run_frac >= 0.6f) c.mode = kModeRuns;
     else if (!force && c.near_frac >= 0.75f && wide_ok) c.mode = kModeRunsWide;
+    // fixed-point scale: 2^e = the power of two above the largest sampled |w|
+    {
+        double inv_q = 0.0, q = 0.0, wcap = 0.0;
+        if (wmax > 0.0) {
+            const int e = ilogb(wmax) + 1;
+            if (e > -900 && e < 40) { q = scalbn(1.0, e - 45); inv_q = scalbn(1.0, 45 - e); wcap = scalbn(1.0, e); }
+        }
+        cfg->fx_inv_q = inv_q;
+        cfg->fx_q = q;
+        cfg->fx_wcap = wcap;
+    }
     cfg->mode = c.mode;
     for (int a = 0; a < 3; ++a) cfg->ext[a] = c.ext[a];
     cfg->est_hit = c.est_hit;
@@ -196,14 +296,23 @@ struct Window {
     int e[3];      // extent
 };
 
-template <int ND, int TT>
+template <int ND, int TT, bool FX>
 __device__ __forceinline__ void flush_tile(double *tile, const Window &wd, const DepositParams &P, int cells,
-                                           int replicas) {
+                                           int replicas, double fx_q) {
     // merge the tile (all its replicas) into the global grid, coalesced along the last axis, and clear it
     for (int c = threadIdx.x; c < cells; c += TT) {
-        double v = tile[c];
-        tile[c] = 0.0;
-        for (int r = 1; r < replicas; ++r) { v = __dadd_rn(v, tile[r * cells + c]); tile[r * cells + c] = 0.0; }
+        double v;
+        if constexpr (FX) {
+            // replicas are summed as integers (exact), one conversion and one multiply by the quantum (a power of two)
+            unsigned *lo = reinterpret_cast<unsigned *>(tile);
+            long long k = fx_take(lo, c);
+            for (int r = 1; r < replicas; ++r) k += fx_take(lo, r * cells + c);
+            v = __dmul_rn(__ll2double_rn(k), fx_q);
+        } else {
+            v = tile[c];
+            tile[c] = 0.0;
+            for (int r = 1; r < replicas; ++r) { v = __dadd_rn(v, tile[r * cells + c]); tile[r * cells + c] = 0.0; }
+        }
         if (v != 0.0) {
             int64_t lin;
             if (ND == 1) lin = wd.o[0] + c;
@@ -221,16 +330,20 @@ __device__ __forceinline__ void flush_tile(double *tile, const Window &wd, const
     }
 }
 
-template <int ND, int S, bool W, int TT, bool F>
+template <int ND, int S, bool W, int TT, bool F, bool FX>
 __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, const TileConfig *cfgp) {
     extern __shared__ double tile[];
     __shared__ long long scratch[34];
     __shared__ Window s_win;
-    __shared__ unsigned s_acc, s_miss;
+    __shared__ unsigned s_acc, s_miss, s_full;
     constexpr int NW = StencilWidth<S>::value;
 
+    if (cfgp->mode != kModeTiled) return;
     const TileConfig cfg = *cfgp;
-    if (cfg.mode != kModeTiled) return;
+    // fixed point: scale, weight cap and this lane's share of the tile's 64-bit range (see fx_lane_limit)
+    const double fx_inv_q = cfg.fx_inv_q, fx_q = cfg.fx_q, fx_wcap = cfg.fx_wcap;
+    const double fx_limit = fx_lane_limit(TT, kEvalEvery * kTV) * fx_wcap;
+    double fx_sum = 0.0;
     int cells = 1;
     bool whole = true;                       // the window holds the whole grid (small 1-D / 2-D histograms)
     for (int a = 0; a < ND; ++a) { cells *= cfg.ext[a]; whole = whole && cfg.ext[a] >= P.dims[a]; }
@@ -240,55 +353,72 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
     if (replicas > TT / 32) replicas = TT / 32;
     if (replicas < 1) replicas = 1;
     double *mytile = tile + ((threadIdx.x >> 5) % replicas) * cells;
+    unsigned *mylo = reinterpret_cast<unsigned *>(tile) + ((threadIdx.x >> 5) % replicas) * cells;
 
-    for (int c = threadIdx.x; c < cells * replicas; c += TT) tile[c] = 0.0;
+    if constexpr (FX) {
+        unsigned *lo = reinterpret_cast<unsigned *>(tile);
+        for (int c = threadIdx.x; c < cells * replicas; c += TT) { lo[c] = 0u; lo[kFxHi + c] = 0u; }
+    } else {
+        for (int c = threadIdx.x; c < cells * replicas; c += TT) tile[c] = 0.0;
+    }
     if (threadIdx.x == 0) {
         for (int a = 0; a < 3; ++a) { s_win.e[a] = a < ND ? cfg.ext[a] : 1; s_win.o[a] = 0; }
         // a window that covers the whole axis never needs to move; the others start "nowhere"
         for (int a = 0; a < ND; ++a) if (cfg.ext[a] < P.dims[a]) s_win.o[a] = -(1 << 28);
-        s_acc = 0; s_miss = 0;
+        s_acc = 0; s_miss = 0; s_full = 0;
     }
     __syncthreads();
     Window wd = s_win;
 
-    // contiguous span of this CTA, a multiple of the CTA width
+    // contiguous span of this CTA, a multiple of the sub-chunk (kTV consecutive particles per lane)
     int64_t per = (P.n + gridDim.x - 1) / gridDim.x;
-    per = (per + TT - 1) / TT * TT;
+    per = (per + TT * kTV - 1) / (TT * kTV) * (TT * kTV);
     const int64_t begin = (int64_t)blockIdx.x * per;
     const int64_t end = begin + per < P.n ? begin + per : P.n;
     const int lane = threadIdx.x & 31;
     const double *px = P.p[0], *py = P.p[1], *pz = P.p[2];
     const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2];
+    // 256-bit loads (one sector per lane and array) when every streamed array is contiguous and 32-byte aligned
+    bool vec = sx == 1 && (reinterpret_cast<uintptr_t>(px) & 31u) == 0;
+    if (ND >= 2) vec = vec && sy == 1 && (reinterpret_cast<uintptr_t>(py) & 31u) == 0;
+    if (ND >= 3) vec = vec && sz == 1 && (reinterpret_cast<uintptr_t>(pz) & 31u) == 0;
+    if (W && !F) vec = vec && P.stride[3] == 1 && (reinterpret_cast<uintptr_t>(P.p[3]) & 31u) == 0;
 
-    // software pipeline: the raw values of the next sub-chunk are in flight while this one is deposited
-    double nx = 0, ny = 0, nz = 0, nwt = 1.0;
-    {
-        const int64_t i = begin + threadIdx.x;
-        if (i < end) {
-            nx = ld_stream(px + i * sx);
-            if (ND >= 2) ny = ld_stream(py + i * sy);
-            if (ND >= 3) nz = ld_stream(pz + i * sz);
-            if (W) nwt = particle_weight<F>(P, i);
-        }
-    }
     int since_eval = kEvalEvery - 1;       // first evaluation right after the first sub-chunk
     unsigned acc_w = 0, miss_w = 0;        // per-warp counters (lane 0), published at evaluation time
-    for (int64_t i0 = begin; i0 < end; i0 += TT) {
-        const int64_t i = i0 + threadIdx.x;
-        const double x = nx, y = ny, z = nz, w = nwt;
-        {
-            const int64_t j = i + TT;
-            if (j < end) {
-                nx = ld_stream(px + j * sx);
-                if (ND >= 2) ny = ld_stream(py + j * sy);
-                if (ND >= 3) nz = ld_stream(pz + j * sz);
-                if (W) nwt = particle_weight<F>(P, j);
+    for (int64_t i0 = begin; i0 < end; i0 += (int64_t)TT * kTV) {
+        const int64_t ib = i0 + (int64_t)threadIdx.x * kTV;
+        double xv[kTV], yv[kTV], zv[kTV], wv[kTV];
+        if (vec && ib + kTV <= end) {
+            tile_ld4(px + ib, xv);
+            if (ND >= 2) tile_ld4(py + ib, yv);
+            if (ND >= 3) tile_ld4(pz + ib, zv);
+            if (W && !F) tile_ld4(P.p[3] + ib, wv);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kTV; ++j) {
+                const bool in = ib + j < end;
+                xv[j] = in ? ld_stream(px + (ib + j) * sx) : 0.0;
+                if (ND >= 2) yv[j] = in ? ld_stream(py + (ib + j) * sy) : 0.0;
+                if (ND >= 3) zv[j] = in ? ld_stream(pz + (ib + j) * sz) : 0.0;
+                if (W && !F) wv[j] = in ? ld_stream(P.p[3] + (ib + j) * P.stride[3]) : 0.0;
             }
         }
+        if constexpr (W && F) {
+#pragma unroll
+            for (int j = 0; j < kTV; ++j) wv[j] = ib + j < end ? particle_weight<F>(P, ib + j) : 0.0;
+        }
+        bool ok = false;                   // (of the lane's last particle: seeds the window after a move)
+        int b[3] = {0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < kTV; ++j) {
+        const int64_t i = ib + j;
+        const double x = xv[j], y = ND >= 2 ? yv[j] : 0.0, z = ND >= 3 ? zv[j] : 0.0, w = W ? wv[j] : 1.0;
         // ---- stencil in registers --------------------------------------------------
-        int b[3];
         double wx[NW], wy[NW], wz[NW];
-        const bool ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) && i < end && particle_selected(P, i);
+        ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) && i < end && particle_selected(P, i);
+        // fixed point takes weights up to the cap (NaN / inf fail the comparison); the others go to the grid exactly
+        const bool fits = !FX || (fx_inv_q != 0.0 && (!W || fabs(w) <= fx_wcap));
         // value of stencil cell (a, c, d), reference operation order: ((wx*wy)*wz)*w
         auto value = [&](int a, int c, int d) -> double { return stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w); };
         constexpr int NV = ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW;
@@ -306,9 +436,9 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
 #pragma unroll
                     for (int d = 0; d < NDD; ++d) v[(a * NC + c) * NDD + d] = value(a, c, d);
             // ---- warp aggregation of runs of equal base cells -------------------------
-            const int key = ok ? (ND == 1 ? b[0] : ND == 2 ? b[0] * P.dims[1] + b[1]
-                                                           : (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2])
-                               : -1 - lane;
+            const int key = ok && fits ? (ND == 1 ? b[0] : ND == 2 ? b[0] * P.dims[1] + b[1]
+                                                                   : (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2])
+                                       : -1 - lane;         // (a particle that does not fit is a run of its own)
             const int prev = __shfl_up_sync(0xffffffffu, key, 1);
             const bool head = lane == 0 || prev != key;
             const unsigned heads = __ballot_sync(0xffffffffu, head);
@@ -332,18 +462,21 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
             else return value(a, c, d);
         };
         // ---- deposit: tile if the stencil fits the window, else straight to the grid ----
-        bool hit = commit;
+        bool hit = commit && fits;
 #pragma unroll
         for (int a = 0; a < ND; ++a) hit = hit && b[a] >= wd.o[a] && b[a] + NW <= wd.o[a] + wd.e[a];
         if (hit) {
             const int p1 = ND >= 2 ? wd.e[1] : 1, p2 = ND >= 3 ? wd.e[2] : 1;
-            double *t = mytile + ((b[0] - wd.o[0]) * p1 + (ND >= 2 ? b[1] - wd.o[1] : 0)) * p2 + (ND >= 3 ? b[2] - wd.o[2] : 0);
+            const int off = ((b[0] - wd.o[0]) * p1 + (ND >= 2 ? b[1] - wd.o[1] : 0)) * p2 + (ND >= 3 ? b[2] - wd.o[2] : 0);
 #pragma unroll
             for (int a = 0; a < NA; ++a)
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
 #pragma unroll
-                    for (int d = 0; d < NDD; ++d) atomicAdd(t + (a * p1 + c) * p2 + d, cellval(a, c, d));
+                    for (int d = 0; d < NDD; ++d) {
+                        if constexpr (FX) fx_add(mylo, off + (a * p1 + c) * p2 + d, cellval(a, c, d), fx_inv_q);
+                        else atomicAdd(mytile + off + (a * p1 + c) * p2 + d, cellval(a, c, d));
+                    }
         } else if (commit) {
             const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
             double *g = P.grid + ((int64_t)b[0] * g1 + b[1]) * g2 + b[2];
@@ -362,18 +495,30 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
         const unsigned m_in = __ballot_sync(0xffffffffu, inside);
         acc_w += __popc(m_ok);
         miss_w += __popc(m_ok & ~m_in);
-        if (++since_eval == kEvalEvery && i0 + TT < end) {
+        // what this lane's particle may have added to a cell of the tile (whoever committed it)
+        if (FX && inside && fits) fx_sum = __dadd_rn(fx_sum, W ? fabs(w) : 1.0);
+      }
+        if (++since_eval == kEvalEvery && i0 + (int64_t)TT * kTV < end) {
             since_eval = 0;
-            if (threadIdx.x == 0) { s_acc = 0; s_miss = 0; }
+            if (threadIdx.x == 0) { s_acc = 0; s_miss = 0; s_full = 0; }
             __syncthreads();
             if (lane == 0 && acc_w) { atomicAdd(&s_acc, acc_w); atomicAdd(&s_miss, miss_w); }
+            if (FX && fx_sum > 0.0 && fx_sum >= fx_limit) s_full = 1u;
             acc_w = 0; miss_w = 0;
             __syncthreads();
             const unsigned acc = s_acc, miss = s_miss;
             const bool move = acc >= 64 && miss * 2 > acc;
+            const bool full = FX && s_full != 0u;
             __syncthreads();
+            if (full && !move) {
+                // the tile's 64-bit range could be exhausted before the next check: merge it, keep the window
+                flush_tile<ND, TT, FX>(tile, wd, P, cells, replicas, fx_q);
+                fx_sum = 0.0;
+                __syncthreads();
+            }
             if (move) {
-                flush_tile<ND, TT>(tile, wd, P, cells, replicas);
+                fx_sum = 0.0;
+                flush_tile<ND, TT, FX>(tile, wd, P, cells, replicas, fx_q);
                 // new centre: mean base cell of the sub-chunk in registers
                 const long long cnt = block_sum(ok ? 1 : 0, scratch);
                 long long mean[3] = {0, 0, 0};
@@ -394,7 +539,242 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
         }
     }
     __syncthreads();
-    flush_tile<ND, TT>(tile, wd, P, cells, replicas);
+    flush_tile<ND, TT, FX>(tile, wd, P, cells, replicas, fx_q);
+}
+
+// ---------------------------------------------------------------------------------
+// the fixed-point tile kernel (the default of method TILED for grids larger than the tile)
+// ---------------------------------------------------------------------------------
+// The same window scheme as k_deposit_tiled, cut down to what the native 32-bit atomics need: no warp
+// aggregation of runs (a same-address collision costs one extra pass of a native atomic, not a CAS retry,
+// and input with long runs is method RUNS' job), the stencil products are formed on the fly right in front
+// of their two atomics, hit / miss statistics live in two registers per lane and are voted on with
+// __syncthreads_count.  This keeps a 2-D TSC instance at 64 registers -- 32 warps per SM, which is what
+// the shared-memory atomic pipe needs to stay busy (the general kernel with the fixed-point adds bolted on:
+// 80 registers + spills at 24 warps, 72 Gp/s on x-ordered cfg2; profiles/r02/perf_fx_variants.log).
+template <int NW>
+__device__ __forceinline__ double pick_w(const double (&wl)[NW], int j) {
+    double v = wl[0];
+#pragma unroll
+    for (int k = 1; k < NW; ++k) v = j == k ? wl[k] : v;
+    return v;
+}
+
+// Deposit `count` (<= 8) queued particles (x, y, z, w per entry) straight into the grid with all 32 lanes: 4 lanes per
+// particle, lane j of a group takes cell j of every stencil row along the last axis (the pattern of k_deposit_quads);
+// the products keep the reference's operation order.
+template <int ND, int S, bool W>
+__device__ __forceinline__ void drain_rows(const DepositParams &P, const double *q, int count, int lane) {
+    constexpr int NW = StencilWidth<S>::value;
+    const int g = lane >> 2, j = lane & 3;
+    if (g >= count || j >= NW) return;
+    const double *e = q + g * 4;
+    int b[3];
+    double wx[NW], wy[NW], wz[NW];
+    if (!particle_stencil<ND, S>(P, e[0], e[1], e[2], b, wx, wy, wz)) return;      // (accepted when it was queued)
+    const double w = e[3];
+    const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
+    double *cell = P.grid + ((int64_t)b[0] * g1 + b[1]) * g2 + b[2] + j;
+    if (ND == 1) {
+        red_add(cell, W ? __dmul_rn(pick_w<NW>(wx, j), w) : pick_w<NW>(wx, j));
+    } else if (ND == 2) {
+        const double wl = pick_w<NW>(wy, j);
+#pragma unroll
+        for (int a = 0; a < NW; ++a) {
+            const double c = __dmul_rn(wx[a], wl);
+            red_add(cell + a * g1, W ? __dmul_rn(c, w) : c);
+        }
+    } else {
+        const double wl = pick_w<NW>(wz, j);
+#pragma unroll
+        for (int a = 0; a < NW; ++a)
+#pragma unroll
+            for (int c2 = 0; c2 < NW; ++c2) {
+                const double c = __dmul_rn(__dmul_rn(wx[a], wy[c2]), wl);
+                red_add(cell + (a * g1 + c2) * g2, W ? __dmul_rn(c, w) : c);
+            }
+    }
+}
+
+#ifndef PTG_FX_THREADS_9
+#define PTG_FX_THREADS_9 1024
+#endif
+template <int ND, int S> struct FxThreads {
+    static constexpr int NW = StencilWidth<S>::value;
+    static constexpr int NV = ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW;
+    static constexpr int value = NV <= 4 ? 1024 : NV <= 9 ? PTG_FX_THREADS_9 : NV <= 16 ? 768 : 512;
+};
+
+template <int ND, int S, bool W, bool F>
+__global__ void __launch_bounds__((FxThreads<ND, S>::value), 1) k_deposit_tile_fx(const DepositParams P, const TileConfig *cfgp) {
+    constexpr int TT = FxThreads<ND, S>::value;
+    // sub-chunks between two evaluations: small stencils leave room in the 64-bit range for twice the interval
+    constexpr int EV = FxThreads<ND, S>::NV <= 9 ? 2 * kEvalEvery : kEvalEvery;
+    extern __shared__ double tile[];
+    __shared__ long long scratch[34];
+    __shared__ Window s_win;
+    constexpr int NW = StencilWidth<S>::value;
+    constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
+
+    if (cfgp->mode != kModeTiled) return;
+    const double fx_inv_q = cfgp->fx_inv_q, fx_q = cfgp->fx_q, fx_wcap = cfgp->fx_wcap;
+    const double fx_limit = fx_lane_limit(TT, EV * kTV) * fx_wcap;
+    double fx_sum = 0.0;
+    unsigned *const lo = reinterpret_cast<unsigned *>(tile);
+    // Particles that miss the window (the thin background around a bunch) are not deposited by the lane that
+    // found them -- 1 lane in 10 would drag its whole warp through (S+1)^ndim uncoalesced REDs -- but parked in a
+    // per-warp queue behind the tile and deposited 8 at a time by all 32 lanes, 4 lanes per particle, each lane
+    // one cell of a stencil row: the sector-coalesced pattern of method ROWS (3 instead of 9 L2 sector
+    // reductions per 2-D TSC particle).
+    constexpr bool QUEUE = S >= 1;
+    constexpr int kQCap = 16;              // entries per warp (at most 7 left over + 8 new)
+    double *const wq = tile + kTileCells + (threadIdx.x >> 5) * (kQCap * 4);
+    int qcount = 0;                        // warp-uniform
+    const int lane = threadIdx.x & 31;
+    int cells = 1;
+    for (int a = 0; a < ND; ++a) cells *= cfgp->ext[a];
+    for (int c = threadIdx.x; c < cells; c += TT) { lo[c] = 0u; lo[kFxHi + c] = 0u; }
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 3; ++a) { s_win.e[a] = a < ND ? cfgp->ext[a] : 1; s_win.o[a] = 0; }
+        // a window that covers the whole axis never needs to move; the others start "nowhere"
+        for (int a = 0; a < ND; ++a) if (cfgp->ext[a] < P.dims[a]) s_win.o[a] = -(1 << 28);
+    }
+    __syncthreads();
+    Window wd = s_win;
+
+    int64_t per = (P.n + gridDim.x - 1) / gridDim.x;
+    per = (per + TT * kTV - 1) / (TT * kTV) * (TT * kTV);
+    const int64_t begin = (int64_t)blockIdx.x * per;
+    const int64_t end = begin + per < P.n ? begin + per : P.n;
+    const double *px = P.p[0], *py = P.p[1], *pz = P.p[2];
+    const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2];
+    bool vec = sx == 1 && (reinterpret_cast<uintptr_t>(px) & 31u) == 0;
+    if (ND >= 2) vec = vec && sy == 1 && (reinterpret_cast<uintptr_t>(py) & 31u) == 0;
+    if (ND >= 3) vec = vec && sz == 1 && (reinterpret_cast<uintptr_t>(pz) & 31u) == 0;
+    if (W && !F) vec = vec && P.stride[3] == 1 && (reinterpret_cast<uintptr_t>(P.p[3]) & 31u) == 0;
+    const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
+
+    int since_eval = EV - 1;       // first evaluation right after the first sub-chunk
+    unsigned n_ok = 0, n_miss = 0;         // this lane's particles since the last evaluation
+    for (int64_t i0 = begin; i0 < end; i0 += (int64_t)TT * kTV) {
+        const int64_t ib = i0 + (int64_t)threadIdx.x * kTV;
+        double xv[kTV], yv[kTV], zv[kTV], wv[kTV];
+        if (vec && ib + kTV <= end) {
+            tile_ld4(px + ib, xv);
+            if (ND >= 2) tile_ld4(py + ib, yv);
+            if (ND >= 3) tile_ld4(pz + ib, zv);
+            if (W && !F) tile_ld4(P.p[3] + ib, wv);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kTV; ++j) {
+                const bool in = ib + j < end;
+                xv[j] = in ? ld_stream(px + (ib + j) * sx) : 0.0;
+                if (ND >= 2) yv[j] = in ? ld_stream(py + (ib + j) * sy) : 0.0;
+                if (ND >= 3) zv[j] = in ? ld_stream(pz + (ib + j) * sz) : 0.0;
+                if (W && !F) wv[j] = in ? ld_stream(P.p[3] + (ib + j) * P.stride[3]) : 0.0;
+            }
+        }
+        if constexpr (W && F) {
+#pragma unroll
+            for (int j = 0; j < kTV; ++j) wv[j] = ib + j < end ? particle_weight<F>(P, ib + j) : 0.0;
+        }
+        bool ok = false;                   // (of the lane's last particle: seeds the window after a move)
+        int b[3] = {0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < kTV; ++j) {
+            const int64_t i = ib + j;
+            const double w = W ? wv[j] : 1.0;
+            double wx[NW], wy[NW], wz[NW];
+            ok = particle_stencil<ND, S>(P, xv[j], ND >= 2 ? yv[j] : 0.0, ND >= 3 ? zv[j] : 0.0, b, wx, wy, wz) &&
+                 i < end && particle_selected(P, i);
+            bool direct = false;           // this particle goes to the grid exactly (misses the window / too heavy)
+            if (ok) {
+            bool inside = true;
+#pragma unroll
+            for (int a = 0; a < ND; ++a) inside = inside && b[a] >= wd.o[a] && b[a] + NW <= wd.o[a] + wd.e[a];
+            ++n_ok;
+            // the tile takes weights up to the cap (NaN / inf fail the comparison); the rest goes to the grid exactly
+            if (inside && fx_inv_q != 0.0 && (!W || fabs(w) <= fx_wcap)) {
+                const int p1 = ND >= 2 ? wd.e[1] : 1, p2 = ND >= 3 ? wd.e[2] : 1;
+                const int off = ((b[0] - wd.o[0]) * p1 + (ND >= 2 ? b[1] - wd.o[1] : 0)) * p2 + (ND >= 3 ? b[2] - wd.o[2] : 0);
+#pragma unroll
+                for (int a = 0; a < NA; ++a)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+#pragma unroll
+                        for (int d = 0; d < NDD; ++d)
+                            fx_add(lo, off + (a * p1 + c) * p2 + d, stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w), fx_inv_q);
+                fx_sum = __dadd_rn(fx_sum, W ? fabs(w) : 1.0);
+            } else {
+                if (!inside) ++n_miss;
+                direct = true;
+            }
+            }
+            // ---- particles for the exact path: queue them (few) or deposit them right here (many) ----
+            const unsigned dm = __ballot_sync(0xffffffffu, direct);
+            if (dm == 0u) continue;
+            if (QUEUE && __popc(dm) <= 8) {
+                if (direct) {
+                    double *e = wq + (qcount + __popc(dm & ((1u << lane) - 1u))) * 4;
+                    e[0] = xv[j];
+                    e[1] = ND >= 2 ? yv[j] : 0.0;
+                    e[2] = ND >= 3 ? zv[j] : 0.0;
+                    e[3] = w;
+                }
+                qcount += __popc(dm);
+                __syncwarp();
+                if (qcount >= 8) {
+                    qcount -= 8;
+                    drain_rows<ND, S, W>(P, wq + qcount * 4, 8, lane);
+                    __syncwarp();
+                }
+            } else if (direct) {
+                double *g = P.grid + ((int64_t)b[0] * g1 + b[1]) * g2 + b[2];
+#pragma unroll
+                for (int a = 0; a < NA; ++a)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+#pragma unroll
+                        for (int d = 0; d < NDD; ++d)
+                            red_add(g + (a * g1 + c) * g2 + d, stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w));
+            }
+        }
+        if (++since_eval == EV && i0 + (int64_t)TT * kTV < end) {
+            since_eval = 0;
+            // lanes whose particles mostly missed the window vote for a move; any lane near its share of the
+            // tile's 64-bit range asks for a merge
+            const int votes = __syncthreads_count(n_miss * 2 > n_ok);
+            const int full = __syncthreads_or(fx_sum > 0.0 && fx_sum >= fx_limit);
+            n_ok = 0; n_miss = 0;
+            const bool move = votes * 2 > TT;
+            if (move || full) {
+                fx_sum = 0.0;
+                flush_tile<ND, TT, true>(tile, wd, P, cells, 1, fx_q);
+                __syncthreads();
+            }
+            if (move) {
+                // new centre: mean base cell of the particles in registers
+                const long long cnt = block_sum(ok ? 1 : 0, scratch);
+                long long mean[3] = {0, 0, 0};
+                for (int a = 0; a < ND; ++a) mean[a] = block_sum(ok ? b[a] : 0, scratch) / (cnt > 0 ? cnt : 1);
+                if (threadIdx.x == 0) {
+                    for (int a = 0; a < ND; ++a) {
+                        if (wd.e[a] >= P.dims[a]) { s_win.o[a] = 0; continue; }
+                        long long o = mean[a] + NW / 2 - wd.e[a] / 2;
+                        if (a == ND - 1) o &= ~1ll;
+                        if (o < 0) o = 0;
+                        if (o > P.dims[a] - wd.e[a]) o = P.dims[a] - wd.e[a];
+                        s_win.o[a] = (int)o;
+                    }
+                }
+                __syncthreads();
+                wd = s_win;
+            }
+        }
+    }
+    if (QUEUE && qcount > 0) drain_rows<ND, S, W>(P, wq, qcount, lane);
+    __syncthreads();
+    flush_tile<ND, TT, true>(tile, wd, P, cells, 1, fx_q);
 }
 
 // ---------------------------------------------------------------------------------
@@ -406,29 +786,35 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
 // replicas into the global grid at the end.  This is the path of postpic's 1-D energy spectra.
 constexpr int kST = 1024;     // threads per CTA, one CTA per SM
 constexpr int kSU = 4;        // particles in flight per thread
+constexpr int kSCheck = 4;    // fixed point: main-loop iterations between two range checks
 
-template <int ND, int S, bool W, bool F>
+template <int ND, int S, bool W, bool F, bool FX>
 __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P, const TileConfig *gate) {
-    if (gate != nullptr && gate->mode != kModeTiled) return;
+    if (gate->mode != kModeTiled) return;
     extern __shared__ double tile[];
     constexpr int NW = StencilWidth<S>::value;
     constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
     // Plain counting (shape 0, no weights -- numpy.histogram's job): every contribution is exactly 1,
-    // so the tile holds 32-bit counters and uses the one NATIVE shared-memory atomic of sm_100a
-    // (ATOMS.ADD.U32, 3.7x the rate of the fp64 CAS loop); the counts are exact and are converted to
+    // so the tile holds 32-bit counters and uses one native shared-memory atomic per particle
+    // (ATOMS.ADD.U32); the counts are exact and are converted to
     // double at the merge.  A CTA sees fewer than 2^32 particles for any n < 148 * 2^32.
     constexpr bool COUNT = (S == 0 && !W);
+    constexpr bool FXA = FX && !COUNT;          // 64-bit fixed point for everything else
     const int cells = P.dims[0] * P.dims[1] * P.dims[2];
     int replicas = kTileCells / cells;
     if (replicas > kST / 32) replicas = kST / 32;
     if (replicas < 1) replicas = 1;
     unsigned *ctile = reinterpret_cast<unsigned *>(tile);
     if (COUNT) { for (int c = threadIdx.x; c < cells * replicas; c += kST) ctile[c] = 0u; }
+    else if (FXA) { for (int c = threadIdx.x; c < cells * replicas; c += kST) { ctile[c] = 0u; ctile[kFxHi + c] = 0u; } }
     else       { for (int c = threadIdx.x; c < cells * replicas; c += kST) tile[c] = 0.0; }
     __syncthreads();
     double *mine = tile + ((threadIdx.x >> 5) % replicas) * cells;
     unsigned *cmine = ctile + ((threadIdx.x >> 5) % replicas) * cells;
     const int p1 = ND >= 2 ? P.dims[1] : 1, p2 = ND >= 3 ? P.dims[2] : 1;
+    double fx_inv_q = 0.0, fx_q = 0.0, fx_wcap = 0.0, fx_sum = 0.0;
+    if (FXA) { fx_inv_q = gate->fx_inv_q; fx_q = gate->fx_q; fx_wcap = gate->fx_wcap; }
+    const double fx_limit = fx_lane_limit(kST, kSCheck * kSU) * fx_wcap;
 
     auto one = [&](double x, double y, double z, double w) {
         int b[3];
@@ -439,22 +825,60 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
             atomicAdd(cmine + (b[0] * p1 + b[1]) * p2 + b[2], 1u);
             return;
         }
-        double *t = mine + (b[0] * p1 + b[1]) * p2 + b[2];
+        const int off = (b[0] * p1 + b[1]) * p2 + b[2];
+        if constexpr (FXA) {
+            if (!(fx_inv_q != 0.0 && (!W || fabs(w) <= fx_wcap))) {
+                // outside the fixed-point range (or NaN / inf): exact reductions straight into the grid
+#pragma unroll
+                for (int a = 0; a < NA; ++a)
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+#pragma unroll
+                        for (int d = 0; d < NDD; ++d)
+                            red_add(P.grid + off + (a * p1 + c) * p2 + d, stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w));
+                return;
+            }
+            fx_sum = __dadd_rn(fx_sum, W ? fabs(w) : 1.0);
+        }
 #pragma unroll
         for (int a = 0; a < NA; ++a)
 #pragma unroll
             for (int c = 0; c < NC; ++c)
 #pragma unroll
                 for (int d = 0; d < NDD; ++d) {
-                    atomicAdd(t + (a * p1 + c) * p2 + d, stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w));
+                    const double v = stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w);
+                    if constexpr (FXA) fx_add(cmine, off + (a * p1 + c) * p2 + d, v, fx_inv_q);
+                    else atomicAdd(mine + off + (a * p1 + c) * p2 + d, v);
                 }
+    };
+    // merge all replicas into the grid (and clear them: the fixed-point tile is merged whenever its range runs out)
+    auto merge = [&]() {
+        for (int c = threadIdx.x; c < cells; c += kST) {
+            double v;
+            if (COUNT) {
+                unsigned long long k = ctile[c];
+                for (int r = 1; r < replicas; ++r) k += ctile[r * cells + c];
+                v = (double)k;
+            } else if (FXA) {
+                long long k = fx_take(ctile, c);
+                for (int r = 1; r < replicas; ++r) k += fx_take(ctile, r * cells + c);
+                v = __dmul_rn(__ll2double_rn(k), fx_q);
+            } else {
+                v = tile[c];
+                for (int r = 1; r < replicas; ++r) v = __dadd_rn(v, tile[r * cells + c]);
+            }
+            if (v != 0.0) red_add(P.grid + c, v);
+        }
     };
 
     const int64_t nthreads = (int64_t)gridDim.x * kST;
-    int64_t i = (int64_t)blockIdx.x * kST + threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * kST + threadIdx.x;
     const double *px = P.p[0], *py = P.p[1], *pz = P.p[2];
     const int64_t sx = P.stride[0], sy = P.stride[1], sz = P.stride[2];
-    for (; i + (kSU - 1) * nthreads < P.n; i += kSU * nthreads) {
+    // the same number of full iterations for every thread of the grid (the range checks below are CTA-wide)
+    const int64_t full = P.n / (kSU * nthreads);
+    for (int64_t it = 0; it < full; ++it) {
+        const int64_t i = base + it * kSU * nthreads;
         double x[kSU], y[kSU], z[kSU], w[kSU];
 #pragma unroll
         for (int u = 0; u < kSU; ++u) {
@@ -467,46 +891,51 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
 #pragma unroll
         for (int u = 0; u < kSU; ++u)
             if (particle_selected(P, i + u * nthreads)) one(x[u], y[u], z[u], w[u]);
+        if (FXA && (it % kSCheck) == kSCheck - 1) {
+            if (__syncthreads_or(fx_sum > 0.0 && fx_sum >= fx_limit)) {
+                merge();
+                fx_sum = 0.0;
+                __syncthreads();
+            }
+        }
     }
-    for (; i < P.n; i += nthreads)
+    // at most kSU particles per lane are left
+    for (int64_t i = base + full * kSU * nthreads; i < P.n; i += nthreads)
         if (particle_selected(P, i)) one(ld_stream(px + i * sx), ND >= 2 ? ld_stream(py + i * sy) : 0.0, ND >= 3 ? ld_stream(pz + i * sz) : 0.0,
             W ? particle_weight<F>(P, i) : 1.0);
     __syncthreads();
-    for (int c = threadIdx.x; c < cells; c += kST) {
-        double v;
-        if (COUNT) {
-            unsigned long long k = ctile[c];
-            for (int r = 1; r < replicas; ++r) k += ctile[r * cells + c];
-            v = (double)k;
-        } else {
-            v = tile[c];
-            for (int r = 1; r < replicas; ++r) v = __dadd_rn(v, tile[r * cells + c]);
-        }
-        if (v != 0.0) red_add(P.grid + c, v);
-    }
+    merge();
 }
 
 // ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
-template <int ND, int S, bool W>
+template <int ND, int S, bool W, bool FX>
 static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int force, int sm_count, cudaStream_t st) {
     constexpr int NW = StencilWidth<S>::value;
     constexpr int TT = TileThreads<(ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW)>::value;
     const bool fuse = W && P.fuse_kind != 0;
-    auto kern = fuse ? k_deposit_tiled<ND, S, W, TT, W> : k_deposit_tiled<ND, S, W, TT, false>;
+    auto kern = fuse ? k_deposit_tiled<ND, S, W, TT, W, false> : k_deposit_tiled<ND, S, W, TT, false, false>;
     const size_t smem = (size_t)kTileCells * sizeof(double);
     // per-device attribute, cheap to set: done on every launch so that any device works
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k_probe<ND, S><<<kProbeBlocks, kTT, 0, st>>>(P, cfg, force, runs_wide_available(ND, S) ? 1 : 0);
+    k_probe<ND, S><<<kProbeBlocks, kTT, 0, st>>>(P, cfg, force, runs_wide_available(ND, S) ? 1 : 0, FX ? 0 : 1);
     if ((int64_t)P.dims[0] * P.dims[1] * P.dims[2] <= kTileCells) {
         // the whole padded grid fits the tile: lean kernel without window management
-        auto small = fuse ? k_deposit_small<ND, S, W, W> : k_deposit_small<ND, S, W, false>;
+        auto small = fuse ? k_deposit_small<ND, S, W, W, FX> : k_deposit_small<ND, S, W, false, FX>;
         e = cudaFuncSetAttribute(small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int64_t want = (P.n + (int64_t)kST * kSU - 1) / ((int64_t)kST * kSU);
         small<<<(int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count), kST, smem, st>>>(P, cfg);
+        return cudaGetLastError();
+    }
+    if constexpr (FX) {
+        auto lean = fuse ? k_deposit_tile_fx<ND, S, W, W> : k_deposit_tile_fx<ND, S, W, false>;
+        const size_t smem_fx = smem + (size_t)(FxThreads<ND, S>::value / 32) * 16 * 4 * sizeof(double);   // + the miss queues
+        e = cudaFuncSetAttribute(lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fx);
+        if (e != cudaSuccess) return e;
+        lean<<<sm_count, FxThreads<ND, S>::value, smem_fx, st>>>(P, cfg);
         return cudaGetLastError();
     }
     kern<<<sm_count, TT, smem, st>>>(P, cfg);
@@ -514,27 +943,29 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
 }
 
 template <int ND, int S>
-static cudaError_t tiled_w(const DepositParams &P, TileConfig *cfg, int force, int sm, cudaStream_t st) {
-    return (P.p[3] || P.fuse_kind) ? launch_tiled<ND, S, true>(P, cfg, force, sm, st) : launch_tiled<ND, S, false>(P, cfg, force, sm, st);
+static cudaError_t tiled_w(const DepositParams &P, TileConfig *cfg, int force, bool exact, int sm, cudaStream_t st) {
+    const bool w = P.p[3] || P.fuse_kind;
+    if (exact) return w ? launch_tiled<ND, S, true, false>(P, cfg, force, sm, st) : launch_tiled<ND, S, false, false>(P, cfg, force, sm, st);
+    return w ? launch_tiled<ND, S, true, true>(P, cfg, force, sm, st) : launch_tiled<ND, S, false, true>(P, cfg, force, sm, st);
 }
 
 template <int ND>
-static cudaError_t tiled_s(int shape, const DepositParams &P, TileConfig *cfg, int force, int sm, cudaStream_t st) {
+static cudaError_t tiled_s(int shape, const DepositParams &P, TileConfig *cfg, int force, bool exact, int sm, cudaStream_t st) {
     switch (shape) {
-        case 0: return tiled_w<ND, 0>(P, cfg, force, sm, st);
-        case 1: return tiled_w<ND, 1>(P, cfg, force, sm, st);
-        case 2: return tiled_w<ND, 2>(P, cfg, force, sm, st);
-        default: return tiled_w<ND, 3>(P, cfg, force, sm, st);
+        case 0: return tiled_w<ND, 0>(P, cfg, force, exact, sm, st);
+        case 1: return tiled_w<ND, 1>(P, cfg, force, exact, sm, st);
+        case 2: return tiled_w<ND, 2>(P, cfg, force, exact, sm, st);
+        default: return tiled_w<ND, 3>(P, cfg, force, exact, sm, st);
     }
 }
 
-cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, int sm_count,
-                          cudaStream_t st) {
+cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, bool exact,
+                          int sm_count, cudaStream_t st) {
     if (P.n <= 0) return cudaSuccess;
     switch (ndim) {
-        case 1: return tiled_s<1>(shape, P, cfg, force, sm_count, st);
-        case 2: return tiled_s<2>(shape, P, cfg, force, sm_count, st);
-        default: return tiled_s<3>(shape, P, cfg, force, sm_count, st);
+        case 1: return tiled_s<1>(shape, P, cfg, force, exact, sm_count, st);
+        case 2: return tiled_s<2>(shape, P, cfg, force, exact, sm_count, st);
+        default: return tiled_s<3>(shape, P, cfg, force, exact, sm_count, st);
     }
 }
 

@@ -22,8 +22,14 @@ struct TileConfig {
     float near_frac;   // ... whose base cells differ by at most one cell forward on every axis
     unsigned ticket;   // probe CTAs that have finished (reset to 0 by the last one)
     int pad;
+    // 64-bit fixed-point accumulation in shared memory (method TILED): a contribution v is added as
+    // round(v * fx_inv_q) quanta on two native 32-bit shared atomics.  fx_q = 2^(e - 45) where 2^e is the
+    // power of two above the largest |weight| the probe sampled; particles with |w| > fx_wcap = 2^e take
+    // the exact RED.F64 path.  fx_inv_q == 0: fixed point unavailable for this launch (no sample, zero or
+    // extreme weights) -- every particle takes the exact path.
+    double fx_inv_q, fx_q, fx_wcap;
     // per-probe-CTA partial statistics
-    struct Part { float mad[3]; int cnt; int eq_pairs; int all_pairs; int near_pairs; int pad; } part[kProbeBlocks];
+    struct Part { float mad[3]; int cnt; int eq_pairs; int all_pairs; int near_pairs; int pad; double wmax; } part[kProbeBlocks];
 };
 
 // ptg_deposit_global.cu -- `gate` (nullable): the kernels return at once unless gate->mode is
@@ -32,8 +38,9 @@ cudaError_t deposit_global(int ndim, int shape, const DepositParams &P, bool row
                            int sm_count, cudaStream_t st);
 
 // ptg_deposit_tiled.cu -- probe + tiled kernel; `force` ignores the probe's verdict
-cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, int sm_count,
-                          cudaStream_t st);
+// `exact`: accumulate the tile in fp64 (CAS loops) instead of 64-bit fixed point
+cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, bool exact,
+                          int sm_count, cudaStream_t st);
 
 // ptg_deposit_runs.cu -- run-length accumulation in registers for cell-ordered input
 // (`wide`: the variant whose register window is one cell wider per axis, mode kModeRunsWide)

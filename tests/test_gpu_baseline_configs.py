@@ -48,11 +48,11 @@ def cloud(name, order, n=None, seed=None):
     nd, shape, bins, ranges = CONFIGS[name]
     rng = np.random.default_rng({"cfg2": 2, "cfg3": 3, "cfg4": 4, "cfg5": 5}[name] if seed is None else seed)
     coords = []
+    pick = rng.random(n) < 0.9 if name == "cfg5" else None      # 90 % of the particles in 1 % of the cells
     for a in range(nd):
         lo, hi = ranges[a]
         u = rng.random(n)
-        if name == "cfg5":
-            pick = rng.random(n) < 0.9
+        if pick is not None:
             u = np.where(pick, 0.45 + 0.1 * u, u)
         coords.append(lo + (hi - lo) * u)
     extra = {}

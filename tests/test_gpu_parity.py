@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "ptg_golden.npz"))
 ALL = [(nd, s, w) for nd in (1, 2, 3) for s in (0, 1, 2, 3) for w in (False, True)]
-METHODS = [None, 'global', 'rows', 'tiled', 'sorted', 'runs', 'runs_wide']
+METHODS = [None, 'global', 'rows', 'tiled', 'tiled_exact', 'sorted', 'runs', 'runs_wide']
 
 
 def _skip_unavailable(method, nd, shape):
@@ -440,7 +440,9 @@ def test_auto_probe_verdicts():
     assert _lib.last_probe()['mode'] == 'rows'                       # i.i.d. over a grid >> tile
     o = torch.argsort(x)
     device.deposit([x[o], y[o]], None, shape=2, **kw)
-    assert _lib.last_probe()['mode'] == 'rows'                       # x-ordered: a band of whole rows is no win
+    assert _lib.last_probe()['mode'] == 'tiled'                      # x-ordered: a band of whole rows in the fixed-point tile
+    device.deposit([x[o], y[o]], None, shape=2, method='auto_exact', **kw)
+    assert _lib.last_probe()['mode'] == 'rows'                       # ... but no win with the fp64 CAS tile
     cell = (x * 1024).floor() * 1024 + (y * 1024).floor()
     o = torch.argsort(cell)
     xs, ys = x[o].contiguous(), y[o].contiguous()
