@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the block with every BASELINE config / shape at full size")
     ap.add_argument("--fused", action="store_true", help="weights = weight * Ekin_MeV(px,py,pz) evaluated inside the deposit kernel (48 B/particle in 2-D)")
     ap.add_argument("--unweighted", action="store_true", help="weights=None (the reference's separate branch)")
     ap.add_argument("--shape", type=int, default=None, help="override the workload's particle shape")
@@ -212,8 +213,9 @@ def load_cpu_impl():
     return ptg_oracle, "port"
 
 
-def cpu_call(mod, name, coords, w):
-    nd, shape, _, bins, ranges, _ = WORKLOADS[name]
+def cpu_call(mod, name, coords, w, shape=None):
+    nd, shape0, _, bins, ranges, _ = WORKLOADS[name]
+    shape = shape0 if shape is None else shape
     if nd == 1:
         return mod.histogram(coords[0], range=ranges[0], bins=bins[0], weights=w, shape=shape)
     if nd == 2:
@@ -256,19 +258,22 @@ def time_cpu_all_cores(name, sample_n):
         return {"value": None, "error": str(exc)}
 
 
-def time_cpu(name, sample_n, repeats=3):
+def time_cpu(name, coords, w, shape, repeats=3):
+    """The reference on one host core over the given host arrays (a slice of the timed cloud); returns the
+    baseline record and the histogram of the last run (the per-bin parity check of the GPU result)."""
     mod, kind = load_cpu_impl()
-    coords, w = make_cloud_host(name, int(sample_n), 2)
-    cpu_call(mod, name, [c[:100000] for c in coords], w[:100000])
+    sample_n = len(coords[0])
+    cpu_call(mod, name, [c[:100000] for c in coords], None if w is None else w[:100000], shape)
     best = 1e30
+    h = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        cpu_call(mod, name, coords, w)
+        h = cpu_call(mod, name, coords, w, shape)[0]
         best = min(best, time.perf_counter() - t0)
     return {"value": sample_n / best * 1e-9, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "first %.3g particles of the workload, best of %d, %s, %d logical cpus on the box"
+            "sample": "first %.3g particles of the timed cloud, best of %d, %s, %d logical cpus on the box"
                       % (sample_n, repeats, cpu_model(), os.cpu_count()),
-            "all_cores": time_cpu_all_cores(name, 4 * sample_n)}
+            "all_cores": time_cpu_all_cores(name, 4 * sample_n)}, h
 
 
 def run_reference_arm(args):
@@ -309,10 +314,25 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # the B200 arm
 # ------------------------------------------------------------------------------------------
+def kernel_name(verdict, nd, shape, weighted, n, plan, fused=False):
+    """The kernel of libptg_b200 that does the work for an AUTO verdict (mirrors the dispatch in
+    csrc/ptg_deposit_*.cu; used to label the roofline and to look up the ncu-measured DRAM traffic)."""
+    nw = 1 if shape == 0 else shape + 1
+    if verdict == "tiled":
+        return "k_deposit_small" if plan.cells <= 25600 else "k_deposit_tile_fx"
+    if verdict == "runs":
+        return "k_deposit_runs_bulk" if (nw ** nd <= 16 and not fused) else "k_deposit_runs"
+    if verdict == "runs_wide":
+        return "k_deposit_runs_wide"
+    if shape == 0:
+        return "k_deposit_global"
+    return "k_deposit_quads" if (nd >= 2 and shape in (1, 2) and not fused) else "k_deposit_rows"
+
+
 def launches_per_step(method, nd, shape, n, plan):
-    """Kernels of libptg_b200 launched per deposit call (checked against the ncu launch list in
-    profiles/r01/launches_cfg2_auto_final_summary.txt): AUTO = probe + tiled + runs (+ runs_wide where
-    it exists) + rows (+ the merge of the staggered staging grid); memsets are not kernels."""
+    """Kernels of libptg_b200 launched per deposit call (checked against the ncu launch lists in profiles/):
+    AUTO = probe + tiled + runs (+ runs_wide where it exists) + rows (+ the merge of the staggered staging
+    grid); memsets are not kernels."""
     nw = 1 if shape == 0 else shape + 1
     wide = (nw + 1) ** nd <= 27
     last = plan.dims[-1]
@@ -322,16 +342,98 @@ def launches_per_step(method, nd, shape, n, plan):
     rows = passes * (2 if stagger else 1)
     if method in ("rows",):
         return rows
-    if method == "auto":
+    if method in ("auto", "auto_exact"):
         if n < (1 << 21):
             return 2 if plan.cells <= 25600 else rows
         return 1 + 1 + 1 + (1 if wide else 0) + rows
-    if method == "tiled":
+    if method in ("tiled", "tiled_exact"):
         return 2
     if method == "sorted":
         passes = -(-max(plan.cells.bit_length(), 1) // 8)
         return 2 + 4 * passes + 2 * nw ** nd   # keys, offsets, 4 sort kernels per 8-bit pass, two reduce launches per colour
     return 1
+
+
+def load_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6650 GB/s (of fallback)"
+
+
+def lookup_traffic(kernel, nd, shape, n):
+    """ncu-measured DRAM bytes per particle of `kernel` (profiles/traffic.json, one `ncu --set full` capture per
+    kernel) scaled to this launch's particle count; None when that kernel instance has not been captured."""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        ent = tr.get("%s/%dd/shape%d" % (kernel, nd, shape))
+        if ent:
+            return int(ent["dram_bytes_per_particle"] * n)
+    except Exception:
+        pass
+    return None
+
+
+def device_time(fn, steps, warm=3):
+    """ms per call of fn(), CUDA events on the launching (current) stream after `warm` warm-up calls."""
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def measure_config(tag, name, n, order, method, dev, peak, shape=None, fused=False, steps=5, extra=None):
+    """One line of the `configs` block: a BASELINE.json configuration (or a shape / size variant of the headline) at
+    full single-GPU size, device-resident, device-timed (zero grid + deposit per step, inputs larger than L2)."""
+    import torch
+    from postpic_b200 import _lib, device as ptgdev
+    nd, s0, _, bins, ranges, desc = WORKLOADS[name]
+    shape = s0 if shape is None else shape
+    coords, w = make_cloud_device(name, n, 2, order, dev)
+    plan = ptgdev.Plan(list(ranges), list(bins), shape)
+    grid = torch.empty(plan.dims, dtype=torch.float64, device=dev)
+    bpp = BYTES_PER_PARTICLE[nd]
+    fz = None
+    if fused:
+        me, c0 = 9.1093837015e-31, 299792458.0
+        g2 = torch.Generator(device=dev).manual_seed(77)
+        mom = [0.1 * me * c0 * torch.randn(n, dtype=torch.float64, device=dev, generator=g2) for _ in range(3)]
+        fz = dict(kind='Ekin_MeV', px=mom[0], py=mom[1], pz=mom[2], mass=me, c=c0)
+        w = torch.ones(n, dtype=torch.float64, device=dev)
+        bpp += 24
+    m = None if method == "auto" else method
+    ms = device_time(lambda: ptgdev.deposit_into(grid, plan, coords, w, method=m, zero=True, fused=fz), steps)
+    out = {"workload": name, "particles": n, "shape": shape, "order": order, "method": method, "value": n / ms * 1e-6,
+           "unit": UNIT, "ms_per_step": ms, "roofline_frac": n * bpp / ms * 1e-6 / peak, "bytes_per_particle": bpp}
+    if method == "auto" and n >= (1 << 21):
+        try:
+            v = _lib.last_probe()["mode"]
+            out["kernel"] = kernel_name(v, nd, shape, True, n, plan, fused)
+        except Exception:
+            pass
+    if fz is None:
+        tot = float(w.sum())
+        out["mass_rel_err"] = abs(float(grid.sum()) - tot) / tot
+    if extra == "reproducible":
+        # bit-reproducibility across 3 runs of the deterministic method (SURVEY.md section 8d, cfg5)
+        ref = grid.clone()
+        same = True
+        for _ in range(2):
+            ptgdev.deposit_into(grid, plan, coords, w, method=m, zero=True)
+            same = same and bool(torch.equal(grid, ref))
+        out["bit_reproducible_3_runs"] = same
+    out["tag"] = tag
+    del coords, w, grid, fz
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_b200_arm(args):
@@ -347,12 +449,15 @@ def run_b200_arm(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    # pinned host buffers (the e2e arm) should sit on the NUMA node of this rank's GPU: bind before allocating
+    numa_cpus = parallel.bind_to_gpu_numa(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     info = _lib.device_info(local_rank)
+    peak, peak_source = load_peak()
 
     name = args.workload
     nd, shape, n_default, bins, ranges, desc = WORKLOADS[name]
@@ -408,18 +513,31 @@ def run_b200_arm(args):
     ms_step = ms_total / args.steps
     value = n * world / (ms_step * 1e-3) * 1e-9
 
-    # the dominant kernel alone: events around each deposit launch on the launching stream
+    probe = None
+    if args.method in ("auto", "auto_exact") and n >= (1 << 21):
+        try:
+            probe = _lib.last_probe()
+        except Exception:
+            probe = None
+    verdict = probe["mode"] if probe else {"global": "rows", "rows": "rows", "tiled": "tiled", "tiled_exact": "tiled",
+                                           "runs": "runs", "runs_wide": "runs_wide"}.get(args.method, "rows")
+    dominant = kernel_name(verdict, nd, shape, w is not None, n, plan, fused is not None)
+    if args.method == "global" or shape == 0 and verdict == "rows":
+        dominant = "k_deposit_global"
+    if args.method == "sorted":
+        dominant = "k_sorted_*"
+
+    # the dominant kernel alone: the launch set of the method the probe chose (AUTO's gated launches of the other
+    # candidates left out), K back-to-back launches between one pair of events on the launching stream
+    k_method = method if method is not None else verdict
+    if args.method == "auto_exact" and verdict == "tiled":
+        k_method = "tiled_exact"
     durs = []
-    for _ in range(args.steps):
+    for _ in range(3):
         grid.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        ptgdev.deposit_into(grid, plan, coords, w, method=method, zero=False, fused=fused)
-        b.record()
-        b.synchronize()
-        durs.append(a.elapsed_time(b))
-    k_ms = sum(durs) / len(durs)
-    k_best, k_median = min(durs), statistics.median(durs)
+        durs.append(device_time(lambda: ptgdev.deposit_into(grid, plan, coords, w, method=k_method, zero=False, fused=fused),
+                                max(args.steps // 2, 3), warm=1))
+    k_ms = statistics.median(durs)
 
     # the exchange step alone (N > 1): one all-reduce of the padded grid, timed like the kernel
     allreduce_ms = None
@@ -436,36 +554,15 @@ def run_b200_arm(args):
         t = torch.tensor([statistics.median(ar)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         allreduce_ms = float(t.item())
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = n * bpp / (k_ms * 1e-3) * 1e-9
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "%s_%s_%s" % (name, args.order, args.method)
-        if key in tr and tr[key].get("n") == n:
-            traffic = tr[key]["dram_bytes_per_launch"]
-    except Exception:
-        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel_ms": k_ms, "kernel_ms_best": k_best, "kernel_ms_median": k_median,
-                "allreduce_ms": allreduce_ms, "allreduce_bytes": plan.cells * 8 if world > 1 else None,
-                "bytes_per_particle": bpp,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                "frac_of_nominal_8TBs": achieved / 8000.0}
+                "traffic": lookup_traffic(dominant, nd, shape, n), "kernel": dominant, "kernel_ms": k_ms,
+                "kernel_ms_best": min(durs), "allreduce_ms": allreduce_ms,
+                "allreduce_bytes": plan.cells * 8 if world > 1 else None, "bytes_per_particle": bpp,
+                "peak_source": peak_source, "frac_of_nominal_8TBs": achieved / 8000.0,
+                "frac_of_read_stream_7000GBs": achieved / 7000.0}
 
-    probe = None
-    if args.method == "auto" and n >= (1 << 21):
-        try:
-            probe = _lib.last_probe()
-        except Exception:
-            probe = None
-
-    # parity spot-check of what was just timed (cheap: mass conservation incl. ghost cells)
+    # parity of what was just timed: mass conservation incl. ghost cells on the full run ...
     if fused is not None:
         tw = ptgdev.kinetic_weights('Ekin_MeV', fused['px'], fused['py'], fused['pz'], w, mass=fused['mass'],
                                     c=fused['c']).sum()
@@ -477,7 +574,27 @@ def run_b200_arm(args):
     step()
     torch.cuda.synchronize()
     dep = float(grid.sum())
-    mass_err = abs(dep - total_w) / total_w
+    parity = {"mass_conservation_rel_err": abs(dep - total_w) / total_w}
+
+    # ... and per bin against the reference on the first `cpu_sample` particles of THIS cloud (rank 0, N = 1): the
+    # CPU baseline below deposits exactly those particles, so its grid is the check
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu and fused is None:
+        m = int(min(args.cpu_sample, n))
+        hc = [c[:m].cpu().numpy() for c in coords]
+        hw = w[:m].cpu().numpy() if w is not None else None
+        cpu, h_ref = time_cpu(name, hc, hw, shape)
+        g_s = torch.empty(plan.dims, dtype=torch.float64, device=dev)
+        ptgdev.deposit_into(g_s, plan, [c[:m] for c in coords], w[:m] if w is not None else None, method=method, zero=True)
+        got = g_s.cpu().numpy()
+        ref = h_ref.base if h_ref.base is not None else h_ref
+        wabs = float(np.abs(hw).sum()) if hw is not None else float(m)
+        parity.update({"checked_particles": m, "against": cpu["kind"],
+                       "per_bin_max_abs_over_max_bin": float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))),
+                       "total_abs_over_sum_abs_w": float(abs(got.sum() - ref.sum()) / wabs),
+                       "tolerance": 1e-12})
+        parity["ok"] = bool(parity["per_bin_max_abs_over_max_bin"] <= 1e-12 and parity["total_abs_over_sum_abs_w"] <= 1e-12)
+        del g_s, got, ref, h_ref, hc, hw
 
     # end to end through the public API with host (pinned) inputs
     e2e = None
@@ -494,10 +611,11 @@ def run_b200_arm(args):
             if world == 1:
                 h, edges = histogramdd(tuple(np_c), weights=np_w, range=ranges, bins=list(bins), shape=shape)
                 return h
-            dc = [c.to(dev, non_blocking=True) for c in hc]
-            dw = hw.to(dev, non_blocking=True) if hw is not None else None
-            g, _ = parallel.deposit_sharded(dc, dw, range=ranges, bins=list(bins), shape=shape, method=method)
-            return g.cpu()
+            # N ranks: each streams ITS block through the chunked H2D pipeline (copy of chunk k+1 overlaps the
+            # deposit of chunk k), one NCCL reduce to rank 0, rank 0 copies the sum back to the host
+            h, _ = parallel.histogram_host_sharded(np_c, np_w, range=ranges, bins=list(bins), shape=shape, method=method,
+                                                   dst=0, device_index=local_rank)
+            return h
         e2e_step()
         barrier()
         t0 = time.perf_counter()
@@ -505,10 +623,19 @@ def run_b200_arm(args):
             e2e_step()
         barrier()
         dt = (time.perf_counter() - t0) / ksteps
+        # this rank's H2D + deposit stage alone -> GB/s over its PCIe link (names the limiter when N ranks copy at once)
+        g_e = torch.empty(plan.dims, dtype=torch.float64, device=dev)
+        barrier()
+        t0 = time.perf_counter()
+        ptgdev.deposit_host_into(g_e, plan, np_c, np_w, method=method, zero=True)
+        h2d_gbs = [n * bpp / (time.perf_counter() - t0) * 1e-9]
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+            allv = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(allv, torch.tensor(h2d_gbs, dtype=torch.float64, device=dev))
+            h2d_gbs = [float(v.item()) for v in allv]
         pageable = None
         if world == 1:
             # the same call on ordinary (pageable) numpy arrays, as a postpic user would pass them
@@ -522,39 +649,47 @@ def run_b200_arm(args):
             del pg_c, pg_w
         e2e = {"value": n * world / dt * 1e-9, "unit": UNIT, "h2d_bytes_per_step": n * bpp, "pageable_value": pageable,
                "d2h_bytes_per_step": plan.cells * 8, "ms_per_step": dt * 1e3, "steps": ksteps,
+               "h2d_deposit_stage_gbs_per_rank": h2d_gbs, "numa_cpus_bound": len(numa_cpus) if numa_cpus else None,
                "api": "postpic_b200.histogramdd(numpy views of pinned host memory)" if world == 1 else
-                      "pinned host -> device copy + postpic_b200.parallel.deposit_sharded + grid D2H"}
+                      "postpic_b200.parallel.histogram_host_sharded(numpy views of pinned host memory): chunked H2D "
+                      "pipeline per rank + NCCL reduce to rank 0 + grid D2H on rank 0"}
+        del hc, hw, np_c, np_w, g_e
 
     # the same workload in the two particle orders PIC dumps come in:
     # device-timed like `value`; reported next to the headline, never instead of it
     variants = None
+    configs = None
     if world == 1 and not args.no_variants and args.order == "random":
         variants = {}
         del coords, w
         torch.cuda.empty_cache()
         for order in ("sorted", "cellsorted"):
-            vc, vw = make_cloud_device(name, n, 2 + rank, order, dev)
-            if args.unweighted:
-                vw = None
-            for _ in range(3):
-                ptgdev.deposit_into(grid, plan, vc, vw, method=method, zero=True)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(args.steps):
-                ptgdev.deposit_into(grid, plan, vc, vw, method=method, zero=True)
-            b.record()
-            b.synchronize()
-            ms = a.elapsed_time(b) / args.steps
+            c = measure_config(order, name, n, order, args.method, dev, peak, shape=shape, steps=args.steps)
             variants["x_sorted" if order == "sorted" else "cell_sorted"] = {
-                "value": n / (ms * 1e-3) * 1e-9, "unit": UNIT, "ms_per_step": ms,
-                "roofline_frac": n * bpp / (ms * 1e-3) * 1e-9 / peak}
-            del vc, vw
-            torch.cuda.empty_cache()
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = time_cpu(name, int(min(args.cpu_sample, n)))
+                "value": c["value"], "unit": UNIT, "ms_per_step": c["ms_per_step"], "roofline_frac": c["roofline_frac"],
+                "kernel": c.get("kernel")}
+    if world == 1 and not args.no_configs and args.order == "random" and name == "cfg2":
+        # every BASELINE.json configuration and every particle shape at full single-GPU size (a few steps each)
+        configs = []
+        plan_ = [("cfg1 as named (1e6 particles: launch bound, us per call matters)", "cfg1", int(1e6), "random", "auto", None, False, 200, None),
+                 ("cfg1 at 1e8 particles", "cfg1", int(1e8), "random", "auto", None, False, 5, None),
+                 ("cfg2 shape 0 (NGP)", "cfg2", int(1e8), "random", "auto", 0, False, 5, None),
+                 ("cfg2 shape 1 (CIC)", "cfg2", int(1e8), "random", "auto", 1, False, 5, None),
+                 ("cfg2 shape 3 (spline3)", "cfg2", int(1e8), "random", "auto", 3, False, 5, None),
+                 ("cfg2 cell-sorted shape 0", "cfg2", int(1e8), "cellsorted", "auto", 0, False, 5, None),
+                 ("cfg2 cell-sorted shape 1", "cfg2", int(1e8), "cellsorted", "auto", 1, False, 5, None),
+                 ("cfg2 cell-sorted shape 3", "cfg2", int(1e8), "cellsorted", "auto", 3, False, 5, None),
+                 ("cfg2 at the north-star size (1e9)", "cfg2", int(1e9), "random", "auto", None, False, 3, None),
+                 ("cfg3 per-GPU share (1.25e8)", "cfg3", int(1.25e8), "random", "auto", None, False, 3, None),
+                 ("cfg4 weights precomputed (5e8)", "cfg4", int(5e8), "random", "auto", None, False, 3, None),
+                 ("cfg4 weight * Ekin_MeV fused (2e8)", "cfg4", int(2e8), "random", "auto", None, True, 3, None),
+                 ("cfg5 AUTO (1e9)", "cfg5", int(1e9), "random", "auto", None, False, 3, None),
+                 ("cfg5 deterministic SORTED (2e8)", "cfg5", int(2e8), "random", "sorted", None, False, 2, "reproducible")]
+        for tag, nm, nn, order, meth, shp, fz, st, extra in plan_:
+            try:
+                configs.append(measure_config(tag, nm, nn, order, meth, dev, peak, shape=shp, fused=fz, steps=st, extra=extra))
+            except Exception as exc:                                   # pragma: no cover
+                configs.append({"tag": tag, "error": str(exc)[:200]})
 
     if rank == 0:
         line = {
@@ -566,10 +701,9 @@ def run_b200_arm(args):
                        "l2": "inputs (%.1f GB per GPU) larger than L2, no flush needed" % (n * bpp * 1e-9),
                        "parallelism": "particles sharded over %d GPU(s), private grids, NCCL all-reduce" % world
                        if world > 1 else "1 GPU", "device": info["name"], "sm_count": info["sm_count"]},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "variants": variants,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "variants": variants, "configs": configs,
             "gpu_launches": args.steps * world * launches_per_step(args.method, nd, shape, n, plan),
-            "clocks": clocks.summary(),
-            "parity": {"mass_conservation_rel_err": mass_err}, "auto_probe": probe,
+            "clocks": clocks.summary(), "parity": parity, "auto_probe": probe,
         }
         print(json.dumps(line))
     if world > 1:

@@ -193,6 +193,17 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n,
                            const int64_t *strides,
                            const double *lo, const double *inv, const int *bins,
                            double *grid, unsigned flags, int device);
+/* The same pipeline with the result left on the device: particles from HOST arrays are streamed through the
+ * staging ring and deposited into the caller's DEVICE grid `grid_device` (on `device`), which is cleared first
+ * when flags has PTG_ZERO_GRID and accumulated into otherwise.  Synchronous: the grid is complete on return.
+ * This is what a multi-GPU caller wants (postpic_b200.parallel.histogram_host_sharded): every rank streams its
+ * own particle block with H2D overlapping the deposit, the grids are then summed over NVLink, and only the
+ * sum crosses PCIe back.                                                                              */
+int ptg_deposit_host_f64(int ndim, int shape, int64_t n,
+                         const double *x, const double *y, const double *z, const double *w,
+                         const int64_t *strides,
+                         const double *lo, const double *inv, const int *bins,
+                         double *grid_device, unsigned flags, int device);
 int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2, int device);
 /* dst_device[i] = src[i * stride] for i in [0, n): host array (pageable or pinned, any element stride)
  * to a contiguous device array through the same threaded pinned staging ring.  Synchronous.  Used when

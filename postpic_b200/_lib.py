@@ -75,6 +75,8 @@ SIGNATURES = {
     "ptg_weights_f64": (_c.c_int, [_c.c_int, _I64, _P, _P, _P, _P, _P, _c.c_double, _c.c_double, _c.c_double, _P, _P]),
     "ptg_histogram_host_f64": (_c.c_int, [_c.c_int, _c.c_int, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                           _c.c_uint, _c.c_int]),
+    "ptg_deposit_host_f64": (_c.c_int, [_c.c_int, _c.c_int, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                        _c.c_uint, _c.c_int]),
     "ptg_minmax_host_f64": (_c.c_int, [_I64, _P, _I64, _P, _c.c_int]),
     "ptg_upload_host_f64": (_c.c_int, [_I64, _P, _I64, _P, _c.c_int]),
     "ptg_release": (_c.c_int, []),

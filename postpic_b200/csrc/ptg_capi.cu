@@ -536,10 +536,16 @@ int ptg_zero_f64(double *grid, int64_t count, void *stream) {
     return PTG_OK;
 }
 
-int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, const double *y,
-                           const double *z, const double *w, const int64_t *strides, const double *lo,
-                           const double *inv, const int *bins, double *grid, unsigned flags, int device) {
-    int rc = validate(ndim, shape, n, x, y, z, lo, inv, bins, grid);
+}  // extern "C"
+
+namespace {
+
+// The host-buffer pipeline behind ptg_histogram_host_f64 (result copied back to the host grid `grid`) and
+// ptg_deposit_host_f64 (result left in / added to the caller's DEVICE grid `dgrid_user`).
+int host_pipeline(int ndim, int shape, int64_t n, const double *x, const double *y,
+                  const double *z, const double *w, const int64_t *strides, const double *lo,
+                  const double *inv, const int *bins, double *grid, double *dgrid_user, unsigned flags, int device) {
+    int rc = validate(ndim, shape, n, x, y, z, lo, inv, bins, dgrid_user ? dgrid_user : grid);
     if (rc) return rc;
     DeviceGuard guard;
     if ((rc = guard.enter(device))) return rc;
@@ -547,7 +553,8 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
     if ((rc = current_device_state(&d))) return rc;
     std::lock_guard<std::mutex> lk(d->mu);
     const int64_t cells = ptg_padded_cells(ndim, shape, bins);
-    if ((rc = ensure_staging(d, cells))) return rc;
+    if ((rc = ensure_staging(d, dgrid_user ? 1 : cells))) return rc;
+    double *const dgrid = dgrid_user ? dgrid_user : d->grid;
     // Sources the copy engine can read directly (page-locked, unit stride) are DMA'd from where they
     // lie.  Anything else -- ordinary pageable numpy memory, strided or reversed views, the columns
     // of an (N, D) array -- is first gathered into a pinned ring by worker threads, chunk k+1 while
@@ -562,7 +569,8 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
     }
     if (!direct && (rc = ensure_pinned(d))) return rc;
 
-    PTG_CUDA(cudaMemsetAsync(d->grid, 0, (size_t)cells * sizeof(double), d->stream[0]));
+    if (!dgrid_user || (flags & PTG_ZERO_GRID))
+        PTG_CUDA(cudaMemsetAsync(dgrid, 0, (size_t)cells * sizeof(double), d->stream[0]));
     Event zeroed;
     PTG_CUDA(zeroed.create());
     PTG_CUDA(cudaEventRecord(zeroed.e, d->stream[0]));
@@ -610,7 +618,7 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
             slot_used[slot] = true;
         }
         rc = deposit_device(d, ndim, shape, m, dptr[0], dptr[1], dptr[2], dptr[3], nullptr, lo, inv, bins,
-                            d->grid, dflags, st);
+                            dgrid, dflags, st);
         if (rc) return rc;
         PTG_CUDA(cudaEventRecord(fin[cidx % kInFlight].e, st));
     }
@@ -621,9 +629,27 @@ int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, cons
         PTG_CUDA(cudaEventRecord(done.e, d->stream[k]));
         PTG_CUDA(cudaStreamWaitEvent(d->stream[0], done.e, 0));
     }
-    PTG_CUDA(cudaMemcpyAsync(grid, d->grid, (size_t)cells * sizeof(double), cudaMemcpyDeviceToHost, d->stream[0]));
+    if (!dgrid_user)
+        PTG_CUDA(cudaMemcpyAsync(grid, dgrid, (size_t)cells * sizeof(double), cudaMemcpyDeviceToHost, d->stream[0]));
     PTG_CUDA(cudaStreamSynchronize(d->stream[0]));
     return PTG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptg_histogram_host_f64(int ndim, int shape, int64_t n, const double *x, const double *y,
+                           const double *z, const double *w, const int64_t *strides, const double *lo,
+                           const double *inv, const int *bins, double *grid, unsigned flags, int device) {
+    return host_pipeline(ndim, shape, n, x, y, z, w, strides, lo, inv, bins, grid, nullptr, flags, device);
+}
+
+int ptg_deposit_host_f64(int ndim, int shape, int64_t n, const double *x, const double *y,
+                         const double *z, const double *w, const int64_t *strides, const double *lo,
+                         const double *inv, const int *bins, double *grid_device, unsigned flags, int device) {
+    if (!grid_device) return fail(PTG_EINVAL, "ptg_deposit_host_f64: grid_device is NULL");
+    return host_pipeline(ndim, shape, n, x, y, z, w, strides, lo, inv, bins, nullptr, grid_device, flags, device);
 }
 
 int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2, int device) {

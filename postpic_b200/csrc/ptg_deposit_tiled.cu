@@ -656,8 +656,13 @@ __global__ void __launch_bounds__((FxThreads<ND, S>::value), 1) k_deposit_tile_f
 
     int since_eval = EV - 1;       // first evaluation right after the first sub-chunk
     unsigned n_ok = 0, n_miss = 0;         // this lane's particles since the last evaluation
+    // (A lane-strided order -- the lanes of a warp thousands of particles apart, so that cell-ordered input does not put
+    // adjacent lanes on one address -- was measured and dropped: cell-ordered input stays at 16 Gp/s either way, because
+    // all warps of the CTA still update the same few cells and same-address shared atomics do not pipeline; such input
+    // is method RUNS' job.  profiles/r02/perf_fx_lanestride.log)
     for (int64_t i0 = begin; i0 < end; i0 += (int64_t)TT * kTV) {
         const int64_t ib = i0 + (int64_t)threadIdx.x * kTV;
+        const bool more = i0 + (int64_t)TT * kTV < end;
         double xv[kTV], yv[kTV], zv[kTV], wv[kTV];
         if (vec && ib + kTV <= end) {
             tile_ld4(px + ib, xv);
@@ -739,7 +744,7 @@ __global__ void __launch_bounds__((FxThreads<ND, S>::value), 1) k_deposit_tile_f
                             red_add(g + (a * g1 + c) * g2 + d, stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w));
             }
         }
-        if (++since_eval == EV && i0 + (int64_t)TT * kTV < end) {
+        if (++since_eval == EV && more) {
             since_eval = 0;
             // lanes whose particles mostly missed the window vote for a move; any lane near its share of the
             // tile's 64-bit range asks for a merge

@@ -144,6 +144,45 @@ def deposit_into(grid, plan, coords, weights=None, method=None, zero=True, strea
     return grid
 
 
+def deposit_host_into(grid, plan, coords, weights=None, method=None, zero=True):
+    """Deposit HOST numpy arrays (float64, any element stride, pageable or pinned) into the padded CUDA tensor
+    `grid` through the library's chunked H2D pipeline (ptg_deposit_host_f64): the copy of chunk k+1 overlaps
+    the deposit of chunk k and the result stays in HBM.  Synchronous."""
+    torch = _torch()
+    lib = _lib.load()
+    if len(coords) != plan.ndim:
+        raise ValueError('expected {} coordinate arrays'.format(plan.ndim))
+    if grid.dtype != torch.float64 or not grid.is_contiguous() or grid.numel() != plan.cells or not grid.is_cuda:
+        raise ValueError('grid must be a contiguous float64 CUDA tensor of {} elements'.format(plan.cells))
+    arrs = []
+    for a, nm in zip(list(coords) + [weights], ['datax', 'datay', 'dataz'][:plan.ndim] + ['weights']):
+        if a is None:
+            arrs.append((None, 1))
+            continue
+        a = np.asarray(a)
+        if a.dtype != np.float64 or a.ndim != 1:
+            raise ValueError('{}: 1-D float64 array expected'.format(nm))
+        if a.shape[0] > 1 and a.strides[0] % 8:
+            a = np.ascontiguousarray(a)
+        arrs.append((a, a.strides[0] // 8 if a.shape[0] > 1 else 1))
+    n = arrs[0][0].shape[0]
+    for a, _ in arrs[:plan.ndim]:
+        if a.shape[0] != n:
+            raise ValueError('datax and datay must be of equal length')
+    w, wstride = arrs[-1]
+    if w is not None and w.shape[0] < n:
+        raise ValueError('weights must have at least as many elements as data')
+    ptr = [a.ctypes.data if n else None for a, _ in arrs[:plan.ndim]] + [None] * (3 - plan.ndim)
+    strides = [st for _, st in arrs[:plan.ndim]] + [1] * (3 - plan.ndim) + [wstride]
+    cstr = (ctypes.c_int64 * 4)(*strides)
+    flags = _lib.METHODS[method] | (_lib.ZERO_GRID if zero else 0)
+    _lib.check(lib.ptg_deposit_host_f64(plan.ndim, plan.shape, n, ptr[0], ptr[1], ptr[2],
+                                        w.ctypes.data if (w is not None and n) else None, cstr,
+                                        plan.lo.ctypes.data, plan.inv.ctypes.data, plan.cbins,
+                                        grid.data_ptr(), flags, grid.device.index))
+    return grid
+
+
 def deposit(coords, weights=None, range=None, bins=None, shape=0, method=None, fused=None, mask=None):
     """-> (padded grid CUDA tensor, plan).  `plan.interior` slices out the histogram."""
     torch = _torch()

@@ -100,3 +100,74 @@ def deposit_sharded(coords, weights=None, range=None, bins=None, shape=2, method
     sum_grids(grid, group=group, dst=dst)
     return grid, plan
 
+
+
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs NVML reports as local to GPU `device_index`, so that the pinned host
+    buffers it allocates afterwards (first touch) and the staging threads of the host pipeline sit on the
+    NUMA node the GPU's PCIe root hangs off.  Returns the CPU list, or None when NVML / the affinity call is
+    not available (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * k + b for k, wd in enumerate(mask) for b in _builtins.range(64) if (wd >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
+def histogram_host_sharded(coords, weights=None, range=None, bins=None, shape=2, method=None, group=None,
+                           dst=0, device_index=None):
+    """The numpy drop-in over R ranks: every rank passes ITS block of the particles as host numpy arrays.
+
+    Each rank streams its block through the library's chunked H2D pipeline into a private padded grid in
+    HBM (ptg_deposit_host_f64: the PCIe copy of chunk k+1 overlaps the deposit of chunk k), the grids are
+    summed with one NCCL reduce to rank `dst` over NVLink (dst=None: all-reduce), and only that rank copies
+    the sum back to the host.  Returns (padded numpy grid or None on the other ranks, plan).  Missing range
+    ends are completed with the global min / max like histogramdd does on one process."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    coords = [np.asarray(c) for c in coords]
+    nd = len(coords)
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    rng = [[None, None] for _ in coords]
+    if range is not None:
+        r = [range] if (nd == 1 and np.isscalar(range[0])) else range
+        for a in _builtins.range(nd):
+            if r[a] is not None:
+                rng[a] = [r[a][0], r[a][1]]
+    missing = [a for a in _builtins.range(nd) if rng[a][0] is None or rng[a][1] is None]
+    if missing:
+        local = []
+        for a in missing:
+            c = coords[a]
+            if c.shape[0] == 0:
+                local.append((float('inf'), float('-inf')))
+                continue
+            out = (ctypes.c_double * 2)()
+            _lib.check(_lib.load().ptg_minmax_host_f64(c.shape[0], c.ctypes.data, c.strides[0] // 8 if c.shape[0] > 1 else 1,
+                                                       out, int(device_index)))
+            local.append((out[0], out[1]))
+        for a, (lo, hi) in zip(missing, global_range(local, group)):
+            rng[a][0] = lo if rng[a][0] is None else rng[a][0]
+            rng[a][1] = hi if rng[a][1] is None else rng[a][1]
+    b = as_bins(bins[0] if (nd == 1 and np.ndim(bins)) else bins, nd)
+    plan = _device.Plan(rng, b, shape)
+    grid = torch.empty(plan.dims, dtype=torch.float64, device=torch.device('cuda', int(device_index)))
+    _device.deposit_host_into(grid, plan, coords, weights, method=method, zero=True)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        sum_grids(grid, group=group, dst=dst)
+        if dst is not None and dist.get_rank(group) != dst:
+            return None, plan
+    return grid.cpu().numpy(), plan

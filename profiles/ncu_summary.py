@@ -20,6 +20,8 @@ KEYS = [
     'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
     'l1tex__t_requests_pipe_lsu_mem_global_op_red.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum',
     'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+    'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_atom.sum',
+    'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum.pct_of_peak_sustained_elapsed',
     'smsp__inst_executed_op_shared_atom.sum', 'smsp__inst_executed_op_shared_atom_dot_cas.sum',
     'smsp__inst_executed_op_global_red.sum', 'smsp__inst_executed.sum', 'smsp__inst_issued.sum',
     'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__inst_executed_pipe_fp64.sum',
