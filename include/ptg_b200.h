@@ -119,6 +119,8 @@ int ptg_minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, voi
 /* grid[i] *= factor for i in [0,count): the h /= dV of particles.py:1101-1102 with
  * factor = 1/dV computed by the caller.                                               */
 int ptg_scale_f64(double *grid, int64_t count, double factor, void *stream);
+/* grid[i] /= divisor with an IEEE division: bit-identical to the reference's `h /= dV`. */
+int ptg_divide_f64(double *grid, int64_t count, double divisor, void *stream);
 int ptg_zero_f64(double *grid, int64_t count, void *stream);
 
 /* ---- per-particle weight expressions in one pass (the step before the path) --------------- */
@@ -133,6 +135,53 @@ int ptg_zero_f64(double *grid, int64_t count, void *stream);
 #define PTG_W_EKIN_MEV 4
 #define PTG_W_EKIN_KEV 5
 #define PTG_W_P        6   /* |p| */
+/* The whole default scalar context of postpic (scalarproperties.py:159-222) as enumerated kinds; 1..6 are the
+ * PTG_W_* above.  Usable as the fused weight factor (fuse_kind) and as fused AXIS expressions (axis_kind[]) of
+ * ptg_deposit_ex_f64, and with ptg_scalar_f64.                                                             */
+#define PTG_S_X 7
+#define PTG_S_Y 8
+#define PTG_S_Z 9
+#define PTG_S_PX 10
+#define PTG_S_PY 11
+#define PTG_S_PZ 12
+#define PTG_S_WEIGHT 13
+#define PTG_S_MASS 14
+#define PTG_S_CHARGE 15
+#define PTG_S_TIME 16
+#define PTG_S_MASS_U 17
+#define PTG_S_CHARGE_E 18
+#define PTG_S_X_UM 19
+#define PTG_S_Y_UM 20
+#define PTG_S_Z_UM 21
+#define PTG_S_NP2 22
+#define PTG_S_GAMMA_M 23
+#define PTG_S_BETA 24
+#define PTG_S_V 25
+#define PTG_S_VX 26
+#define PTG_S_VY 27
+#define PTG_S_VZ 28
+#define PTG_S_BETAX 29
+#define PTG_S_BETAY 30
+#define PTG_S_BETAZ 31
+#define PTG_S_ERUHE 32
+#define PTG_S_EKIN_MEV_AMU 33
+#define PTG_S_EKIN_MEV_QM 34
+#define PTG_S_EKIN_KEV_AMU 35
+#define PTG_S_EKIN_KEV_QM 36
+#define PTG_S_ANGLE_XAXIS 37
+#define PTG_S_ANGLE_YAXIS 38
+#define PTG_S_ANGLE_ZAXIS 39
+#define PTG_S_ANGLE_XY 40
+#define PTG_S_ANGLE_YX 41
+#define PTG_S_ANGLE_YZ 42
+#define PTG_S_ANGLE_ZY 43
+#define PTG_S_ANGLE_ZX 44
+#define PTG_S_ANGLE_XZ 45
+#define PTG_S_R_XY 46
+#define PTG_S_R_YZ 47
+#define PTG_S_R_ZX 48
+#define PTG_S_R_XYZ 49
+#define PTG_S_LAST 49
 int ptg_weights_f64(int kind, int64_t n, const double *px, const double *py, const double *pz,
                     const double *weight, const int64_t *strides, double mass, double c, double elementary_charge,
                     double *out, void *stream);
@@ -174,8 +223,21 @@ typedef struct ptg_deposit_args {
     void *workspace;
     size_t workspace_bytes;
     void *stream;
+    /* ---- fused axis expressions (struct_size tells whether the caller knows these members) ----
+     * axis_kind[a] != 0: coordinate a of every particle is the scalar PTG_S_<kind> evaluated in the kernel from
+     * the atomic arrays pos_x/pos_y/pos_z (positions), px/py/pz (momenta), w (macro-particle weight) and the
+     * species constants; the slot pointer x / y / z of that axis is ignored (may be NULL).  The axis and
+     * `weight * (expr)` evaluations of particles.py:1071,1097 without a single N-sized temporary.          */
+    int axis_kind[3];
+    const double *pos_x, *pos_y, *pos_z;
+    const int64_t *pos_strides;         /* [3] or NULL */
+    double charge, time, atomic_mass;   /* species charge [C], dump time [s], atomic mass unit [kg] */
+    double weight_const;                /* macro-particle weight used when w is NULL (0 is read as 1) */
 } ptg_deposit_args;
 int ptg_deposit_ex_f64(const ptg_deposit_args *args);
+/* out[i] = scalar `kind` (1..PTG_S_LAST) of particle i, evaluated from the atomic arrays of `args` exactly as the
+ * deposit kernels evaluate it (device pointers; only n, the atomic arrays, the constants and stream are read). */
+int ptg_scalar_f64(const ptg_deposit_args *args, int kind, double *out);
 
 /* ---- host-buffer drop-in: H2D + deposit + D2H in one call --------------------------- */
 /*

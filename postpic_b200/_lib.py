@@ -52,7 +52,10 @@ class DepositArgs(_c.Structure):
                 ("bins", _P), ("grid", _P), ("flags", _c.c_uint), ("mask", _P), ("mask_stride", _I64),
                 ("fuse_kind", _c.c_int), ("px", _P), ("py", _P), ("pz", _P), ("pstrides", _P),
                 ("mass", _c.c_double), ("c", _c.c_double), ("elementary_charge", _c.c_double),
-                ("workspace", _P), ("workspace_bytes", _c.c_size_t), ("stream", _P)]
+                ("workspace", _P), ("workspace_bytes", _c.c_size_t), ("stream", _P),
+                ("axis_kind", _c.c_int * 3), ("pos_x", _P), ("pos_y", _P), ("pos_z", _P), ("pos_strides", _P),
+                ("charge", _c.c_double), ("time", _c.c_double), ("atomic_mass", _c.c_double),
+                ("weight_const", _c.c_double)]
 
 
 # name -> (restype, argtypes); every symbol include/ptg_b200.h declares
@@ -67,10 +70,12 @@ SIGNATURES = {
     "ptg_deposit_fused_f64": (_c.c_int, [_c.c_int, _c.c_int, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _c.c_uint,
                                          _c.c_int, _P, _P, _P, _P, _c.c_double, _c.c_double, _c.c_double, _P]),
     "ptg_deposit_ex_f64": (_c.c_int, [_P]),
+    "ptg_scalar_f64": (_c.c_int, [_P, _c.c_int, _P]),
     "ptg_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _I64, _P, _c.c_uint]),
     "ptg_padded_cells": (_I64, [_c.c_int, _c.c_int, _P]),
     "ptg_minmax_f64": (_c.c_int, [_I64, _P, _I64, _P, _P]),
     "ptg_scale_f64": (_c.c_int, [_P, _I64, _c.c_double, _P]),
+    "ptg_divide_f64": (_c.c_int, [_P, _I64, _c.c_double, _P]),
     "ptg_zero_f64": (_c.c_int, [_P, _I64, _P]),
     "ptg_weights_f64": (_c.c_int, [_c.c_int, _I64, _P, _P, _P, _P, _P, _c.c_double, _c.c_double, _c.c_double, _P, _P]),
     "ptg_histogram_host_f64": (_c.c_int, [_c.c_int, _c.c_int, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _P,

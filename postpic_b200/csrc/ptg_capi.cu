@@ -4,6 +4,7 @@
 // staging ring for the host-buffer entry points) and the H2D -> deposit -> D2H
 // pipeline.  No CUDA or C++ type crosses the boundary; nothing here throws.
 #include <cmath>
+#include <cstddef>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -46,6 +47,7 @@ struct DeviceState {
     std::mutex mu;                                // serialises the host-buffer entry points of THIS device
     int sm_count = 0;
     int cc_major = 0, cc_minor = 0;
+    cudaMemPool_t pool = nullptr;                 // the library's private stream-ordered pool on this device
     // host-entry staging
     cudaStream_t stream[kSlots] = {};
     double *slot[kSlots] = {};                    // each 4 * kChunk doubles
@@ -74,6 +76,20 @@ struct Event {
     Event &operator=(const Event &) = delete;
 };
 
+}  // namespace
+
+namespace ptg {
+cudaError_t scratch_alloc(void **ptr, size_t bytes, cudaStream_t st) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    cudaMemPool_t pool = (dev >= 0 && dev < kMaxDevices) ? g_dev[dev].pool : nullptr;
+    return pool ? cudaMallocFromPoolAsync(ptr, bytes, pool, st) : cudaMallocAsync(ptr, bytes, st);
+}
+}  // namespace ptg
+
+namespace {
+
 int probe(int device, DeviceState **out) {
     if (device < 0) {
         cudaError_t e = cudaGetDevice(&device);
@@ -93,14 +109,22 @@ int probe(int device, DeviceState **out) {
             d.sm_count = p.multiProcessorCount;
             d.cc_major = p.major;
             d.cc_minor = p.minor;
-            d.usable = (p.major == 10);           // the library holds sm_100a code only
-            // stream-ordered scratch (staggered staging grid, SORTED workspace) comes from the
-            // device's default memory pool: keep freed blocks cached instead of returning them
-            // to the driver at every synchronisation
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            d.usable = (p.major == 10 && p.minor == 0);   // the library holds sm_100a code only (not sm_103)
+            // stream-ordered scratch (staggered staging grid, SORTED workspace) comes from a memory pool of
+            // the library's own: freed blocks stay cached there instead of going back to the driver at every
+            // synchronisation, and the device's default pool -- which torch's cudaMallocAsync backend or
+            // anything else in the process may use -- keeps its settings
+            cudaMemPoolProps props;
+            memset(&props, 0, sizeof props);
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = device;
+            if (cudaMemPoolCreate(&d.pool, &props) == cudaSuccess) {
                 unsigned long long keep = ~0ull;
-                (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                (void)cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            } else {
+                d.pool = nullptr;                         // fall back to the default pool, untouched
             }
             (void)cudaGetLastError();
             d.probed.store(true, std::memory_order_release);
@@ -153,7 +177,8 @@ void fill_params(ptg::DepositParams &P, int ndim, int shape, int64_t n, const do
     P.stag = nullptr;
     P.stag_pitch = 0;
     P.stag_copy = 0;
-    P.fuse_kind = 0;            // (memset above already cleared q / qstride / f_*)
+    P.fuse_kind = 0;            // (memset above already cleared q / qstride / f_* / akind / pos)
+    P.f_weight = 1.0;
 }
 
 struct FuseSpec {
@@ -161,7 +186,29 @@ struct FuseSpec {
     const double *q[3];
     int64_t qstride[3];
     double mass, c, qe;
+    // axis expressions and the atomic arrays / constants they may read
+    int akind[3] = {0, 0, 0};
+    const double *pos[3] = {nullptr, nullptr, nullptr};
+    int64_t pos_stride[3] = {1, 1, 1};
+    double charge = 0.0, time = 0.0, amu = 1.66053906660e-27, weight_const = 1.0;
 };
+
+// which atomic arrays scalar `kind` reads: bit 0..2 = x, y, z; bit 3 = the momenta
+unsigned scalar_needs(int kind) {
+    if (kind >= 1 && kind <= 6) return 8u;
+    switch (kind) {
+        case PTG_S_X: case PTG_S_X_UM: return 1u;
+        case PTG_S_Y: case PTG_S_Y_UM: return 2u;
+        case PTG_S_Z: case PTG_S_Z_UM: return 4u;
+        case PTG_S_R_XY: return 3u;
+        case PTG_S_R_YZ: return 6u;
+        case PTG_S_R_ZX: return 5u;
+        case PTG_S_R_XYZ: return 7u;
+        case PTG_S_WEIGHT: case PTG_S_MASS: case PTG_S_CHARGE: case PTG_S_TIME: case PTG_S_MASS_U: case PTG_S_CHARGE_E:
+        case PTG_S_ERUHE: return 0u;
+        default: return 8u;
+    }
+}
 
 struct MaskSpec {
     const unsigned char *mask;
@@ -209,6 +256,17 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
         P.f_mc2 = (fuse->mass * fuse->c) * (fuse->mass * fuse->c);
         P.f_c2 = fuse->c * fuse->c;
         P.f_qe = fuse->qe;
+        P.f_c = fuse->c;
+        P.f_charge = fuse->charge;
+        P.f_time = fuse->time;
+        P.f_amu = fuse->amu;
+        P.f_weight = fuse->weight_const;
+        for (int a = 0; a < 3; ++a) {
+            P.akind[a] = a < ndim ? fuse->akind[a] : 0;
+            P.any_akind |= P.akind[a];
+            P.pos[a] = fuse->pos[a];
+            P.pos_stride[a] = fuse->pos_stride[a];
+        }
     }
     if (flags & PTG_ZERO_GRID)
         PTG_CUDA(cudaMemsetAsync(grid, 0, (size_t)ptg_padded_cells(ndim, shape, bins) * sizeof(double), st));
@@ -264,7 +322,7 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
             } else {
                 // no workspace supplied: stream-ordered allocation, released after the last kernel
                 void *ws = nullptr;
-                PTG_CUDA(cudaMallocAsync(&ws, need, st));
+                PTG_CUDA(ptg::scratch_alloc(&ws, need, st));
                 cudaError_t e = ptg::deposit_sorted(ndim, shape, P, ws, need, d->sm_count, st);
                 cudaError_t e2 = cudaFreeAsync(ws, st);
                 PTG_CUDA(e);
@@ -464,7 +522,7 @@ int ptg_deposit_fused_f64(int ndim, int shape, int64_t n, const double *x, const
     if (n > 0 && (!px || !py || !pz)) return fail(PTG_EINVAL, "momentum pointer is NULL");
     DeviceState *d;
     if ((rc = current_device_state(&d))) return rc;
-    FuseSpec f;
+    FuseSpec f{};
     f.kind = kind;
     f.q[0] = px; f.q[1] = py; f.q[2] = pz;
     for (int k = 0; k < 3; ++k) f.qstride[k] = pstrides ? pstrides[k] : 1;
@@ -473,27 +531,106 @@ int ptg_deposit_fused_f64(int ndim, int shape, int64_t n, const double *x, const
                           nullptr, 0, &f);
 }
 
-int ptg_deposit_ex_f64(const ptg_deposit_args *a) {
-    if (!a || a->struct_size < sizeof(ptg_deposit_args)) return fail(PTG_EINVAL, "ptg_deposit_ex_f64: bad argument block");
-    int rc = validate(a->ndim, a->shape, a->n, a->x, a->y, a->z, a->lo, a->inv, a->bins, a->grid);
+}  // extern "C"
+
+namespace {
+
+// the argument block as this build knows it: callers built against the round-1 header pass a shorter struct
+constexpr size_t kArgsV1 = offsetof(ptg_deposit_args, axis_kind);
+
+int read_args(const ptg_deposit_args *in, ptg_deposit_args *a) {
+    if (!in || (in->struct_size != kArgsV1 && in->struct_size < sizeof(ptg_deposit_args)))
+        return fail(PTG_EINVAL, "bad argument block (struct_size)");
+    memset(a, 0, sizeof *a);
+    memcpy(a, in, in->struct_size < sizeof *a ? in->struct_size : sizeof *a);
+    return PTG_OK;
+}
+
+// weight / axis expression set-up shared by ptg_deposit_ex_f64 and ptg_scalar_f64; *fp = nullptr when nothing is fused
+int fuse_from_args(const ptg_deposit_args *a, FuseSpec *f, const FuseSpec **fp, int extra_kind) {
+    *fp = nullptr;
+    unsigned needs = 0;
+    bool any = false;
+    const int kinds[5] = {a->fuse_kind, a->axis_kind[0], a->axis_kind[1], a->axis_kind[2], extra_kind};
+    for (int k = 0; k < 5; ++k) {
+        if (kinds[k] == 0) continue;
+        if (kinds[k] < 1 || kinds[k] > PTG_S_LAST) return fail(PTG_EINVAL, "unknown scalar expression kind %d", kinds[k]);
+        needs |= scalar_needs(kinds[k]);
+        any = true;
+    }
+    if (!any) return PTG_OK;
+    if (a->n > 0) {
+        if ((needs & 8u) && (!a->px || !a->py || !a->pz)) return fail(PTG_EINVAL, "momentum pointer is NULL");
+        if ((needs & 1u) && !a->pos_x) return fail(PTG_EINVAL, "pos_x is NULL but a requested scalar reads x");
+        if ((needs & 2u) && !a->pos_y) return fail(PTG_EINVAL, "pos_y is NULL but a requested scalar reads y");
+        if ((needs & 4u) && !a->pos_z) return fail(PTG_EINVAL, "pos_z is NULL but a requested scalar reads z");
+    }
+    f->kind = a->fuse_kind;
+    f->q[0] = a->px; f->q[1] = a->py; f->q[2] = a->pz;
+    for (int k = 0; k < 3; ++k) f->qstride[k] = a->pstrides ? a->pstrides[k] : 1;
+    f->mass = a->mass;
+    f->c = a->c != 0.0 ? a->c : 299792458.0;
+    f->qe = a->elementary_charge != 0.0 ? a->elementary_charge : 1.602176634e-19;
+    for (int k = 0; k < 3; ++k) f->akind[k] = a->axis_kind[k];
+    f->pos[0] = a->pos_x; f->pos[1] = a->pos_y; f->pos[2] = a->pos_z;
+    for (int k = 0; k < 3; ++k) f->pos_stride[k] = a->pos_strides ? a->pos_strides[k] : 1;
+    f->charge = a->charge;
+    f->time = a->time;
+    if (a->atomic_mass != 0.0) f->amu = a->atomic_mass;
+    f->weight_const = a->weight_const != 0.0 ? a->weight_const : 1.0;
+    *fp = f;
+    return PTG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptg_deposit_ex_f64(const ptg_deposit_args *in) {
+    ptg_deposit_args args;
+    int rc = read_args(in, &args);
+    if (rc) return rc;
+    const ptg_deposit_args *a = &args;
+    // a coordinate slot whose axis is an expression needs no array: give validate() something non-NULL
+    const double *vx = a->axis_kind[0] ? (const double *)a->grid : a->x;
+    const double *vy = a->axis_kind[1] ? (const double *)a->grid : a->y;
+    const double *vz = a->axis_kind[2] ? (const double *)a->grid : a->z;
+    rc = validate(a->ndim, a->shape, a->n, vx, vy, vz, a->lo, a->inv, a->bins, a->grid);
     if (rc) return rc;
     DeviceState *d;
     if ((rc = current_device_state(&d))) return rc;
     FuseSpec f;
     const FuseSpec *fp = nullptr;
-    if (a->fuse_kind != 0) {
-        if (a->fuse_kind < PTG_W_GAMMA_M1 || a->fuse_kind > PTG_W_P)
-            return fail(PTG_EINVAL, "unknown weight expression kind %d", a->fuse_kind);
-        if (a->n > 0 && (!a->px || !a->py || !a->pz)) return fail(PTG_EINVAL, "momentum pointer is NULL");
-        f.kind = a->fuse_kind;
-        f.q[0] = a->px; f.q[1] = a->py; f.q[2] = a->pz;
-        for (int k = 0; k < 3; ++k) f.qstride[k] = a->pstrides ? a->pstrides[k] : 1;
-        f.mass = a->mass; f.c = a->c; f.qe = a->elementary_charge;
-        fp = &f;
-    }
+    if ((rc = fuse_from_args(a, &f, &fp, 0))) return rc;
     MaskSpec m{a->mask, a->mask_stride ? a->mask_stride : 1};
     return deposit_device(d, a->ndim, a->shape, a->n, a->x, a->y, a->z, a->w, a->strides, a->lo, a->inv, a->bins,
                           a->grid, a->flags, (cudaStream_t)a->stream, a->workspace, a->workspace_bytes, fp, &m);
+}
+
+int ptg_scalar_f64(const ptg_deposit_args *in, int kind, double *out) {
+    ptg_deposit_args args;
+    int rc = read_args(in, &args);
+    if (rc) return rc;
+    if (args.n < 0 || (args.n > 0 && !out)) return fail(PTG_EINVAL, "ptg_scalar_f64: bad arguments");
+    DeviceState *d;
+    if ((rc = current_device_state(&d))) return rc;
+    FuseSpec f;
+    const FuseSpec *fp = nullptr;
+    args.fuse_kind = 0;
+    args.axis_kind[0] = args.axis_kind[1] = args.axis_kind[2] = 0;
+    if ((rc = fuse_from_args(&args, &f, &fp, kind))) return rc;
+    if (!fp) return fail(PTG_EINVAL, "unknown scalar expression kind %d", kind);
+    ptg::DepositParams P;
+    const double one = 1.0;
+    const int bins1[3] = {1, 1, 1};
+    fill_params(P, 1, 0, args.n, nullptr, nullptr, nullptr, args.w, args.strides, &one, &one, bins1, nullptr);
+    P.f_mass = f.mass;
+    P.f_mc2 = (f.mass * f.c) * (f.mass * f.c);
+    P.f_c2 = f.c * f.c;
+    P.f_qe = f.qe; P.f_c = f.c; P.f_charge = f.charge; P.f_time = f.time; P.f_amu = f.amu; P.f_weight = f.weight_const;
+    for (int k = 0; k < 3; ++k) { P.q[k] = f.q[k]; P.qstride[k] = f.qstride[k]; P.pos[k] = f.pos[k]; P.pos_stride[k] = f.pos_stride[k]; }
+    PTG_CUDA(ptg::scalar_f64(P, kind, out, d->sm_count, (cudaStream_t)args.stream));
+    return PTG_OK;
 }
 
 int ptg_minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, void *stream) {
@@ -511,6 +648,15 @@ int ptg_scale_f64(double *grid, int64_t count, double factor, void *stream) {
     int rc = current_device_state(&d);
     if (rc) return rc;
     PTG_CUDA(ptg::scale_f64(grid, count, factor, d->sm_count, (cudaStream_t)stream));
+    return PTG_OK;
+}
+
+int ptg_divide_f64(double *grid, int64_t count, double divisor, void *stream) {
+    if (!grid || count < 0) return fail(PTG_EINVAL, "ptg_divide_f64: bad arguments");
+    DeviceState *d;
+    int rc = current_device_state(&d);
+    if (rc) return rc;
+    PTG_CUDA(ptg::divide_f64(grid, count, divisor, d->sm_count, (cudaStream_t)stream));
     return PTG_OK;
 }
 
@@ -670,7 +816,7 @@ int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2
     if (nchunks == 0) { out2[0] = NAN; out2[1] = NAN; return PTG_OK; }
     // every chunk is reduced on the device into its own (min, max) pair; the pairs come home in ONE copy
     double *partials = nullptr;
-    PTG_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&partials), (size_t)nchunks * 16, d->stream[0]));
+    PTG_CUDA(ptg::scratch_alloc(reinterpret_cast<void **>(&partials), (size_t)nchunks * 16, d->stream[0]));
     struct Scratch { double *p; cudaStream_t st; ~Scratch() { cudaFreeAsync(p, st); } } scratch{partials, d->stream[0]};
     PTG_CUDA(cudaStreamSynchronize(d->stream[0]));         // the other ring streams may use it right away
     bool slot_used[kSlots] = {};
@@ -751,7 +897,7 @@ int ptg_release(void) {
         DeviceState &d = g_dev[dev];
         std::lock_guard<std::mutex> lk(d.mu);
         std::lock_guard<std::mutex> lk_ring(g_ring_mu);
-        if (!d.staged && !d.stream[0] && !d.grid && !d.cfg_ring.load()) continue;
+        if (!d.staged && !d.stream[0] && !d.grid && !d.cfg_ring.load() && !d.pool) continue;
         cudaSetDevice(dev);
         cudaDeviceSynchronize();                  // nothing of this device may still read what is freed below
         for (int k = 0; k < kSlots; ++k) {
@@ -765,6 +911,7 @@ int ptg_release(void) {
             d.stream[k] = nullptr;
         }
         if (d.grid) cudaFree(d.grid);
+        if (d.pool) (void)cudaMemPoolTrimTo(d.pool, 0);      // hand the cached scratch back to the driver
         if (d.cfg_ring.load()) cudaFree(d.cfg_ring.load());
         d.cfg_ring.store(nullptr);
         d.grid = nullptr; d.grid_cells = 0; d.staged = false; d.pinned_ready = false;

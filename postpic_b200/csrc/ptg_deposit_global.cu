@@ -63,9 +63,9 @@ __global__ void __launch_bounds__(kThreads) k_deposit_global(const DepositParams
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const int64_t k = i + u * nthreads;
-            x[u] = ld_stream(px + k * sx);
-            y[u] = ND >= 2 ? ld_stream(py + k * sy) : 0.0;
-            z[u] = ND >= 3 ? ld_stream(pz + k * sz) : 0.0;
+            x[u] = particle_coord<F>(P, 0, k);
+            y[u] = ND >= 2 ? particle_coord<F>(P, 1, k) : 0.0;
+            z[u] = ND >= 3 ? particle_coord<F>(P, 2, k) : 0.0;
             w[u] = W ? particle_weight<F>(P, k) : 1.0;
         }
 #pragma unroll
@@ -73,9 +73,9 @@ __global__ void __launch_bounds__(kThreads) k_deposit_global(const DepositParams
             if (particle_selected(P, i + u * nthreads)) deposit_particle_global<ND, S, W>(P, x[u], y[u], z[u], w[u]);
     }
     for (; i < P.n; i += nthreads) {
-        const double x = ld_stream(px + i * sx);
-        const double y = ND >= 2 ? ld_stream(py + i * sy) : 0.0;
-        const double z = ND >= 3 ? ld_stream(pz + i * sz) : 0.0;
+        const double x = particle_coord<F>(P, 0, i);
+        const double y = ND >= 2 ? particle_coord<F>(P, 1, i) : 0.0;
+        const double z = ND >= 3 ? particle_coord<F>(P, 2, i) : 0.0;
         const double w = W ? particle_weight<F>(P, i) : 1.0;
         if (particle_selected(P, i)) deposit_particle_global<ND, S, W>(P, x, y, z, w);
     }
@@ -131,9 +131,9 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
         double w = 1.0;
         bool ok = i < end && particle_selected(P, i);
         if (ok) {
-            const double x = ld_stream(px + i * sx);
-            const double y = ND >= 2 ? ld_stream(py + i * sy) : 0.0;
-            const double z = ND >= 3 ? ld_stream(pz + i * sz) : 0.0;
+            const double x = particle_coord<F>(P, 0, i);
+            const double y = ND >= 2 ? particle_coord<F>(P, 1, i) : 0.0;
+            const double z = ND >= 3 ? particle_coord<F>(P, 2, i) : 0.0;
             if (W) w = particle_weight<F>(P, i);
             int b[3];
             ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) && b[0] >= P.slab_lo && b[0] < P.slab_hi;
@@ -230,9 +230,9 @@ __global__ void __launch_bounds__(kThreads) k_deposit_quads(const DepositParams 
             x[u] = y[u] = z[u] = 0.0;
             w[u] = 1.0;
             if (live[u]) {
-                x[u] = ld_stream(px + i * sx);
-                if (ND >= 2) y[u] = ld_stream(py + i * sy);
-                if (ND >= 3) z[u] = ld_stream(pz + i * sz);
+                x[u] = particle_coord<F>(P, 0, i);
+                if (ND >= 2) y[u] = particle_coord<F>(P, 1, i);
+                if (ND >= 3) z[u] = particle_coord<F>(P, 2, i);
                 if (W) w[u] = particle_weight<F>(P, i);
             }
         }
@@ -300,7 +300,7 @@ static cudaError_t launch_global(const DepositParams &P, const TileConfig *gate,
     int64_t cap = (int64_t)sm_count * 8;                  // 8 x 256 threads = full occupancy
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
-    if (W && P.fuse_kind) k_deposit_global<ND, S, W, W><<<blocks, kThreads, 0, st>>>(P, gate);
+    if (W && fused_mode(P)) k_deposit_global<ND, S, W, W><<<blocks, kThreads, 0, st>>>(P, gate);
     else k_deposit_global<ND, S, W, false><<<blocks, kThreads, 0, st>>>(P, gate);
     return cudaGetLastError();
 }
@@ -317,13 +317,13 @@ static cudaError_t launch_rows(const DepositParams &P, const TileConfig *gate, i
     // of 4 stay staged, and so do the fused-weight variants whose sqrt/divide chain would run G times over).
     // PTG_ROWS_IMPL=q|s forces one of them (A/B runs).
     static const int forced = [] { const char *e = getenv("PTG_ROWS_IMPL"); return !e ? 0 : e[0] == 'q' ? 1 : 2; }();
-    const bool quads = forced ? forced == 1 : (ND >= 2 && (S == 1 || S == 2) && !(W && P.fuse_kind));
+    const bool quads = forced ? forced == 1 : (ND >= 2 && (S == 1 || S == 2) && !(W && fused_mode(P)));
     if (P.stag != nullptr) {
         if constexpr (S == 1 || S == 2) {
             if (quads) {
-                if (W && P.fuse_kind) k_deposit_quads<ND, S, W, true, W><<<blocks, kThreads, 0, st>>>(P, gate);
+                if (W && fused_mode(P)) k_deposit_quads<ND, S, W, true, W><<<blocks, kThreads, 0, st>>>(P, gate);
                 else k_deposit_quads<ND, S, W, true, false><<<blocks, kThreads, 0, st>>>(P, gate);
-            } else if (W && P.fuse_kind) k_deposit_rows<ND, S, W, true, W><<<blocks, kThreads, 0, st>>>(P, gate);
+            } else if (W && fused_mode(P)) k_deposit_rows<ND, S, W, true, W><<<blocks, kThreads, 0, st>>>(P, gate);
             else k_deposit_rows<ND, S, W, true, false><<<blocks, kThreads, 0, st>>>(P, gate);
             const int last = P.dims[ND - 1];
             const int64_t rows = (int64_t)P.dims[0] * P.dims[1] * P.dims[2] / last;
@@ -333,16 +333,16 @@ static cudaError_t launch_rows(const DepositParams &P, const TileConfig *gate, i
         }
     }
     if (quads) {
-        if (W && P.fuse_kind) k_deposit_quads<ND, S, W, false, W><<<blocks, kThreads, 0, st>>>(P, gate);
+        if (W && fused_mode(P)) k_deposit_quads<ND, S, W, false, W><<<blocks, kThreads, 0, st>>>(P, gate);
         else k_deposit_quads<ND, S, W, false, false><<<blocks, kThreads, 0, st>>>(P, gate);
-    } else if (W && P.fuse_kind) k_deposit_rows<ND, S, W, false, W><<<blocks, kThreads, 0, st>>>(P, gate);
+    } else if (W && fused_mode(P)) k_deposit_rows<ND, S, W, false, W><<<blocks, kThreads, 0, st>>>(P, gate);
     else k_deposit_rows<ND, S, W, false, false><<<blocks, kThreads, 0, st>>>(P, gate);
     return cudaGetLastError();
 }
 
 template <int ND, int S>
 static cudaError_t dispatch_w(const DepositParams &P, bool rows, const TileConfig *gate, int sm_count, cudaStream_t st) {
-    const bool weighted = P.p[3] != nullptr || P.fuse_kind != 0;
+    const bool weighted = P.p[3] != nullptr || fused_mode(P);
     if (rows) {
         if constexpr (S >= 1) {
             return weighted ? launch_rows<ND, S, true>(P, gate, sm_count, st) : launch_rows<ND, S, false>(P, gate, sm_count, st);
@@ -410,7 +410,7 @@ cudaError_t deposit_global(int ndim, int shape, const DepositParams &P0, bool ro
         if (rows && !no_stagger && (shape == 1 || shape == 2) && bytes <= ((size_t)64 << 20) && 2 * copy < (int64_t(1) << 31) &&
             P.n >= (int64_t(1) << 20)) {
             void *buf = nullptr;
-            cudaError_t e = cudaMallocAsync(&buf, bytes, st);           // stream-ordered, pooled: no sync
+            cudaError_t e = scratch_alloc(&buf, bytes, st);           // stream-ordered, pooled: no sync
             if (e != cudaSuccess) return e;
             e = cudaMemsetAsync(buf, 0, bytes, st);
             if (e != cudaSuccess) return e;

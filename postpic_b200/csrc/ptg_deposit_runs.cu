@@ -146,7 +146,16 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
 
         double x[kRK], y[kRK], z[kRK], w[kRK];
         auto load_batch = [&](int64_t i0) {
-            if (i0 + kRK <= end) {
+            if (F && P.any_akind) {             // axis expressions: evaluated particle by particle
+#pragma unroll
+                for (int j = 0; j < kRK; ++j) {
+                    const bool in = i0 + j < end;
+                    x[j] = in ? particle_coord<F>(P, 0, i0 + j) : 0.0;
+                    if (ND >= 2) y[j] = in ? particle_coord<F>(P, 1, i0 + j) : 0.0;
+                    if (ND >= 3) z[j] = in ? particle_coord<F>(P, 2, i0 + j) : 0.0;
+                    if (W && P.p[3]) w[j] = in ? P.p[3][(i0 + j) * P.stride[3]] : 0.0;
+                }
+            } else if (i0 + kRK <= end) {
                 load_k<VEC>(P.p[0], P.stride[0], i0, x);
                 if (ND >= 2) load_k<VEC>(P.p[1], P.stride[1], i0, y);
                 if (ND >= 3) load_k<VEC>(P.p[2], P.stride[2], i0, z);
@@ -171,11 +180,13 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
             if constexpr (F) {
                 if (!P.p[3]) {
 #pragma unroll
-                    for (int j = 0; j < kRK; ++j) w[j] = 1.0;
+                    for (int j = 0; j < kRK; ++j) w[j] = P.f_weight;
                 }
+                if (P.fuse_kind != 0) {
 #pragma unroll
-                for (int j = 0; j < kRK; ++j)
-                    if (j < valid) w[j] = __dmul_rn(w[j], fused_factor(P, i0 + j));
+                    for (int j = 0; j < kRK; ++j)
+                        if (j < valid) w[j] = __dmul_rn(w[j], fused_factor(P, i0 + j));
+                }
             }
 #pragma unroll
             for (int j = 0; j < kRK; ++j) {
@@ -482,7 +493,7 @@ static bool bulk_ok(const DepositParams &P) {
     // (profiles/r02/suite_runs_bulk.log).  PTG_RUNS_IMPL=v keeps the vector-load kernel (A/B runs).
     constexpr bool by_default = true;
     if (forced == 2 || (forced == 0 && !by_default)) return false;
-    if (P.mask != nullptr || P.fuse_kind != 0 || P.n < (int64_t(1) << 13)) return false;
+    if (P.mask != nullptr || fused_mode(P) || P.n < (int64_t(1) << 13)) return false;
     for (int k = 0; k < 4; ++k) {
         const bool used = k < ND || (k == 3 && W);
         if (used && (P.stride[k] != 1 || (reinterpret_cast<uintptr_t>(P.p[k]) & 15u))) return false;
@@ -499,7 +510,7 @@ template <int ND, int S> struct WideOk {
 template <int ND, int S, bool W>
 static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, bool wide, int sm_count, cudaStream_t st) {
     if (P.n <= 0) return cudaSuccess;
-    bool vec = true;
+    bool vec = P.any_akind == 0;
     for (int k = 0; k < 4; ++k) {
         const bool used = k < ND || (k == 3 && W && P.p[3] != nullptr);
         if (!used) continue;
@@ -511,7 +522,7 @@ static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, b
     if (blocks < 1) blocks = 1;
     if (wide) {
         if constexpr (WideOk<ND, S>::value) {
-            if (W && P.fuse_kind) {
+            if (W && fused_mode(P)) {
                 if (vec) k_deposit_runs<ND, S, W, true, 1, W><<<blocks, kRT, 0, st>>>(P, gate);
                 else k_deposit_runs<ND, S, W, false, 1, W><<<blocks, kRT, 0, st>>>(P, gate);
             } else {
@@ -522,7 +533,7 @@ static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, b
         return cudaGetLastError();      // (no widened instance for this stencil: nothing launched)
     }
     if (bulk_ok<ND, S, W>(P)) return launch_runs_bulk<ND, S, W>(P, gate, sm_count, st);
-    if (W && P.fuse_kind) {
+    if (W && fused_mode(P)) {
         if (vec) k_deposit_runs<ND, S, W, true, 0, W><<<blocks, kRT, 0, st>>>(P, gate);
         else k_deposit_runs<ND, S, W, false, 0, W><<<blocks, kRT, 0, st>>>(P, gate);
     } else {
@@ -534,7 +545,7 @@ static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, b
 
 template <int ND, int S>
 static cudaError_t runs_w(const DepositParams &P, const TileConfig *gate, bool wide, int sm, cudaStream_t st) {
-    return (P.p[3] || P.fuse_kind) ? launch_runs<ND, S, true>(P, gate, wide, sm, st) : launch_runs<ND, S, false>(P, gate, wide, sm, st);
+    return (P.p[3] || fused_mode(P)) ? launch_runs<ND, S, true>(P, gate, wide, sm, st) : launch_runs<ND, S, false>(P, gate, wide, sm, st);
 }
 
 template <int ND>

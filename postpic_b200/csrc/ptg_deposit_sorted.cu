@@ -30,9 +30,9 @@ __global__ void __launch_bounds__(256) k_cell_keys(const DepositParams P, uint32
                                                     uint32_t *idx) {
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += step) {
-        const double x = ld_stream(P.p[0] + i * P.stride[0]);
-        const double y = ND >= 2 ? ld_stream(P.p[1] + i * P.stride[1]) : 0.0;
-        const double z = ND >= 3 ? ld_stream(P.p[2] + i * P.stride[2]) : 0.0;
+        const double x = particle_coord_rt(P, 0, i);
+        const double y = ND >= 2 ? particle_coord_rt(P, 1, i) : 0.0;
+        const double z = ND >= 3 ? particle_coord_rt(P, 2, i) : 0.0;
         int b[3];
         double wx[StencilWidth<S>::value], wy[StencilWidth<S>::value], wz[StencilWidth<S>::value];
         const bool ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) && particle_selected(P, i);
@@ -94,9 +94,9 @@ __global__ void __launch_bounds__(256) k_segment_reduce(const DepositParams P, c
         for (int k = 0; k < NV; ++k) acc[k] = 0.0;
         for (uint32_t p = s0 + lane; p < s1; p += 32) {
             const int64_t i = idx[p];
-            const double x = P.p[0][i * P.stride[0]];
-            const double y = ND >= 2 ? P.p[1][i * P.stride[1]] : 0.0;
-            const double z = ND >= 3 ? P.p[2][i * P.stride[2]] : 0.0;
+            const double x = particle_coord<F>(P, 0, i);
+            const double y = ND >= 2 ? particle_coord<F>(P, 1, i) : 0.0;
+            const double z = ND >= 3 ? particle_coord<F>(P, 2, i) : 0.0;
             const double w = W ? particle_weight<F>(P, i) : 1.0;
             double wx[NW], wy[NW], wz[NW];
             int b[3];
@@ -199,11 +199,11 @@ static cudaError_t run_sorted(const DepositParams &P, void *ws, size_t ws_bytes,
                 if (ncell <= 0) continue;
                 int64_t wantb = (ncell + 7) / 8;                  // 8 warps per CTA
                 int nb = (int)(wantb < cap * 4 ? wantb : cap * 4);
-                if (W && P.fuse_kind) k_segment_reduce<ND, S, W, false, W><<<nb, 256, 0, st>>>(P, is, off, cx, cy, cz);
+                if (W && fused_mode(P)) k_segment_reduce<ND, S, W, false, W><<<nb, 256, 0, st>>>(P, is, off, cx, cy, cz);
                 else k_segment_reduce<ND, S, W, false, false><<<nb, 256, 0, st>>>(P, is, off, cx, cy, cz);
                 // the long segments of the same colour (clustered input), one CTA each
                 nb = (int)(ncell < cap ? ncell : cap);
-                if (W && P.fuse_kind) k_segment_reduce<ND, S, W, true, W><<<nb, 256, 0, st>>>(P, is, off, cx, cy, cz);
+                if (W && fused_mode(P)) k_segment_reduce<ND, S, W, true, W><<<nb, 256, 0, st>>>(P, is, off, cx, cy, cz);
                 else k_segment_reduce<ND, S, W, true, false><<<nb, 256, 0, st>>>(P, is, off, cx, cy, cz);
             }
     return cudaGetLastError();
@@ -211,7 +211,7 @@ static cudaError_t run_sorted(const DepositParams &P, void *ws, size_t ws_bytes,
 
 template <int ND, int S>
 static cudaError_t sorted_w(const DepositParams &P, void *ws, size_t wsb, int sm, cudaStream_t st) {
-    return (P.p[3] || P.fuse_kind) ? run_sorted<ND, S, true>(P, ws, wsb, sm, st) : run_sorted<ND, S, false>(P, ws, wsb, sm, st);
+    return (P.p[3] || fused_mode(P)) ? run_sorted<ND, S, true>(P, ws, wsb, sm, st) : run_sorted<ND, S, false>(P, ws, wsb, sm, st);
 }
 
 template <int ND>
@@ -234,9 +234,9 @@ cudaError_t selftest_radix_sort(int64_t n, int bits, uint32_t *keys, uint32_t *p
     if (n <= 0) return cudaSuccess;
     uint32_t *k1 = nullptr, *v0 = nullptr;
     void *scratch = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&k1), (size_t)n * 4, st);
-    if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void **>(&v0), (size_t)n * 4, st);
-    if (e == cudaSuccess) e = cudaMallocAsync(&scratch, radix_sort_scratch_bytes(n), st);
+    cudaError_t e = scratch_alloc(reinterpret_cast<void **>(&k1), (size_t)n * 4, st);
+    if (e == cudaSuccess) e = scratch_alloc(reinterpret_cast<void **>(&v0), (size_t)n * 4, st);
+    if (e == cudaSuccess) e = scratch_alloc(&scratch, radix_sort_scratch_bytes(n), st);
     if (e != cudaSuccess) return e;
     k_iota<<<1024, 256, 0, st>>>(v0, n);
     uint32_t *ks = nullptr, *vs = nullptr;

@@ -150,15 +150,15 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
         if (P.n >= 2 * kTT) {
             const int64_t start = (P.n - kTT) / (kProbeBlocks - 1) * blockIdx.x;
             const int64_t i = start + threadIdx.x;
-            const double x = ld_stream(P.p[0] + i * P.stride[0]);
-            const double y = ND >= 2 ? ld_stream(P.p[1] + i * P.stride[1]) : 0.0;
-            const double z = ND >= 3 ? ld_stream(P.p[2] + i * P.stride[2]) : 0.0;
+            const double x = particle_coord_rt(P, 0, i);
+            const double y = ND >= 2 ? particle_coord_rt(P, 1, i) : 0.0;
+            const double z = ND >= 3 ? particle_coord_rt(P, 2, i) : 0.0;
             int b[3];
             const bool ok = base_cells<ND, S>(P, x, y, z, b);
             // largest finite |weight| of the sample: sets the quantum of the fixed-point tile
             double aw = 1.0;
-            if (P.p[3] != nullptr || P.fuse_kind != 0) {
-                aw = P.p[3] != nullptr ? fabs(ld_stream(P.p[3] + i * P.stride[3])) : 1.0;
+            if (P.p[3] != nullptr || fused_mode(P)) {
+                aw = fabs(P.p[3] != nullptr ? ld_stream(P.p[3] + i * P.stride[3]) : P.f_weight);
                 if (P.fuse_kind != 0) aw = fabs(__dmul_rn(aw, fused_factor(P, i)));
                 if (!(aw <= 1.79769313486231570e308)) aw = 0.0;
             }
@@ -383,6 +383,7 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
     if (ND >= 2) vec = vec && sy == 1 && (reinterpret_cast<uintptr_t>(py) & 31u) == 0;
     if (ND >= 3) vec = vec && sz == 1 && (reinterpret_cast<uintptr_t>(pz) & 31u) == 0;
     if (W && !F) vec = vec && P.stride[3] == 1 && (reinterpret_cast<uintptr_t>(P.p[3]) & 31u) == 0;
+    if (F && P.any_akind) vec = false;      // axis expressions are evaluated particle by particle
 
     int since_eval = kEvalEvery - 1;       // first evaluation right after the first sub-chunk
     unsigned acc_w = 0, miss_w = 0;        // per-warp counters (lane 0), published at evaluation time
@@ -398,9 +399,9 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
 #pragma unroll
             for (int j = 0; j < kTV; ++j) {
                 const bool in = ib + j < end;
-                xv[j] = in ? ld_stream(px + (ib + j) * sx) : 0.0;
-                if (ND >= 2) yv[j] = in ? ld_stream(py + (ib + j) * sy) : 0.0;
-                if (ND >= 3) zv[j] = in ? ld_stream(pz + (ib + j) * sz) : 0.0;
+                xv[j] = in ? particle_coord<F>(P, 0, ib + j) : 0.0;
+                if (ND >= 2) yv[j] = in ? particle_coord<F>(P, 1, ib + j) : 0.0;
+                if (ND >= 3) zv[j] = in ? particle_coord<F>(P, 2, ib + j) : 0.0;
                 if (W && !F) wv[j] = in ? ld_stream(P.p[3] + (ib + j) * P.stride[3]) : 0.0;
             }
         }
@@ -652,6 +653,7 @@ __global__ void __launch_bounds__((FxThreads<ND, S>::value), 1) k_deposit_tile_f
     if (ND >= 2) vec = vec && sy == 1 && (reinterpret_cast<uintptr_t>(py) & 31u) == 0;
     if (ND >= 3) vec = vec && sz == 1 && (reinterpret_cast<uintptr_t>(pz) & 31u) == 0;
     if (W && !F) vec = vec && P.stride[3] == 1 && (reinterpret_cast<uintptr_t>(P.p[3]) & 31u) == 0;
+    if (F && P.any_akind) vec = false;      // axis expressions are evaluated particle by particle
     const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
 
     int since_eval = EV - 1;       // first evaluation right after the first sub-chunk
@@ -673,9 +675,9 @@ __global__ void __launch_bounds__((FxThreads<ND, S>::value), 1) k_deposit_tile_f
 #pragma unroll
             for (int j = 0; j < kTV; ++j) {
                 const bool in = ib + j < end;
-                xv[j] = in ? ld_stream(px + (ib + j) * sx) : 0.0;
-                if (ND >= 2) yv[j] = in ? ld_stream(py + (ib + j) * sy) : 0.0;
-                if (ND >= 3) zv[j] = in ? ld_stream(pz + (ib + j) * sz) : 0.0;
+                xv[j] = in ? particle_coord<F>(P, 0, ib + j) : 0.0;
+                if (ND >= 2) yv[j] = in ? particle_coord<F>(P, 1, ib + j) : 0.0;
+                if (ND >= 3) zv[j] = in ? particle_coord<F>(P, 2, ib + j) : 0.0;
                 if (W && !F) wv[j] = in ? ld_stream(P.p[3] + (ib + j) * P.stride[3]) : 0.0;
             }
         }
@@ -888,9 +890,9 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
 #pragma unroll
         for (int u = 0; u < kSU; ++u) {
             const int64_t k = i + u * nthreads;
-            x[u] = ld_stream(px + k * sx);
-            y[u] = ND >= 2 ? ld_stream(py + k * sy) : 0.0;
-            z[u] = ND >= 3 ? ld_stream(pz + k * sz) : 0.0;
+            x[u] = particle_coord<F>(P, 0, k);
+            y[u] = ND >= 2 ? particle_coord<F>(P, 1, k) : 0.0;
+            z[u] = ND >= 3 ? particle_coord<F>(P, 2, k) : 0.0;
             w[u] = W ? particle_weight<F>(P, k) : 1.0;
         }
 #pragma unroll
@@ -906,8 +908,8 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
     }
     // at most kSU particles per lane are left
     for (int64_t i = base + full * kSU * nthreads; i < P.n; i += nthreads)
-        if (particle_selected(P, i)) one(ld_stream(px + i * sx), ND >= 2 ? ld_stream(py + i * sy) : 0.0, ND >= 3 ? ld_stream(pz + i * sz) : 0.0,
-            W ? particle_weight<F>(P, i) : 1.0);
+        if (particle_selected(P, i)) one(particle_coord<F>(P, 0, i), ND >= 2 ? particle_coord<F>(P, 1, i) : 0.0,
+                                         ND >= 3 ? particle_coord<F>(P, 2, i) : 0.0, W ? particle_weight<F>(P, i) : 1.0);
     __syncthreads();
     merge();
 }
@@ -919,7 +921,7 @@ template <int ND, int S, bool W, bool FX>
 static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int force, int sm_count, cudaStream_t st) {
     constexpr int NW = StencilWidth<S>::value;
     constexpr int TT = TileThreads<(ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW)>::value;
-    const bool fuse = W && P.fuse_kind != 0;
+    const bool fuse = W && fused_mode(P);
     auto kern = fuse ? k_deposit_tiled<ND, S, W, TT, W, false> : k_deposit_tiled<ND, S, W, TT, false, false>;
     const size_t smem = (size_t)kTileCells * sizeof(double);
     // per-device attribute, cheap to set: done on every launch so that any device works
@@ -949,7 +951,7 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
 
 template <int ND, int S>
 static cudaError_t tiled_w(const DepositParams &P, TileConfig *cfg, int force, bool exact, int sm, cudaStream_t st) {
-    const bool w = P.p[3] || P.fuse_kind;
+    const bool w = P.p[3] || fused_mode(P);
     if (exact) return w ? launch_tiled<ND, S, true, false>(P, cfg, force, sm, st) : launch_tiled<ND, S, false, false>(P, cfg, force, sm, st);
     return w ? launch_tiled<ND, S, true, true>(P, cfg, force, sm, st) : launch_tiled<ND, S, false, true>(P, cfg, force, sm, st);
 }

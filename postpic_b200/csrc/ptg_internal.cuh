@@ -56,13 +56,19 @@ cudaError_t deposit_sorted(int ndim, int shape, const DepositParams &P, void *ws
 
 cudaError_t selftest_radix_sort(int64_t n, int bits, uint32_t *keys, uint32_t *perm, cudaStream_t st);
 
+// ptg_capi.cu -- stream-ordered scratch from the LIBRARY'S OWN memory pool (freed blocks stay cached there; the
+// device's default pool, which other components of the process may share, is left alone)
+cudaError_t scratch_alloc(void **ptr, size_t bytes, cudaStream_t st);
+
 // ptg_util.cu
 cudaError_t minmax_f64(int64_t n, const double *x, int64_t stride, double *out2, int sm_count,
                        cudaStream_t st);
 cudaError_t scale_f64(double *grid, int64_t count, double factor, int sm_count, cudaStream_t st);
+cudaError_t divide_f64(double *grid, int64_t count, double divisor, int sm_count, cudaStream_t st);
 cudaError_t weights_f64(int kind, int64_t n, const double *px, const double *py, const double *pz,
                         const double *weight, const int64_t *strides, double mass, double c, double qe, double *out,
                         int sm_count, cudaStream_t st);
+cudaError_t scalar_f64(const DepositParams &P, int kind, double *out, int sm_count, cudaStream_t st);
 cudaError_t selftest_div6(int64_t n, const double *in, double *out, cudaStream_t st);
 
 }  // namespace ptg

@@ -122,11 +122,22 @@ struct DepositParams {
     // postpic's filter / compress (particles.py:219-232, :561-582) without materialising compressed copies
     const unsigned char *mask;
     int64_t mstride;
-    int fuse_kind;
+    int fuse_kind;          // scalar (PTG_S_* of ptg_b200.h) the particle weight is multiplied with, 0 = none
+    // fused AXIS expressions (0 = coordinate a is the array p[a]): coordinate a of particle i is the scalar
+    // akind[a] of postpic's default scalar context, evaluated in the kernel from the atomic arrays below --
+    // createField('x_um', 'angle_xy', weights='gamma') is then ONE pass with no N-sized temporary
+    int akind[3];
+    int any_akind;
     const double *q[3];     // px, py, pz
     int64_t qstride[3];
+    const double *pos[3];   // atomic x, y, z (for expression kinds; independent of the coordinate slots p[0..2])
+    int64_t pos_stride[3];
     double f_mass, f_mc2, f_c2, f_qe;   // mass, (mass*c)^2, c^2, elementary charge
+    double f_c, f_charge, f_time, f_amu, f_weight;   // c, species charge, dump time, atomic mass unit, constant macro weight
 };
+
+// the kernels' fused (F = true) instances do the work when a weight or an axis expression is evaluated in the kernel
+__host__ __device__ inline bool fused_mode(const DepositParams &P) { return P.fuse_kind != 0 || P.any_akind != 0; }
 
 __device__ __forceinline__ bool particle_selected(const DepositParams &P, int64_t i) {
 #ifdef PTG_NO_MASK
@@ -204,11 +215,90 @@ __device__ __forceinline__ double kinetic_value(int kind, double x, double y, do
     }
 }
 
-// Weight of particle i for the weighted kernels: the weights array (1 when absent), times the fused
-// kinetic scalar when one is requested.
+// Scalar `kind` (PTG_S_* of ptg_b200.h) of particle i: postpic's default scalar context
+// (/root/reference/postpic/particles/scalarproperties.py:159-222) as enumerated kinds, every expression in the
+// operation order its definition string prescribes (the library is built with -fmad=false: no contraction).
+// The atomic arrays are read through the read-only path; a kind only touches the arrays it needs.
+__device__ __forceinline__ double scalar_value(const DepositParams &P, int kind, int64_t i) {
+    auto X = [&](int a) { return __ldg(P.pos[a] + i * P.pos_stride[a]); };
+    auto Q = [&](int a) { return __ldg(P.q[a] + i * P.qstride[a]); };
+    if (kind <= 6) return kinetic_value(kind, Q(0), Q(1), Q(2), P.f_mass, P.f_mc2, P.f_c2, P.f_qe);
+    switch (kind) {
+        case 7: return X(0);
+        case 8: return X(1);
+        case 9: return X(2);
+        case 10: return Q(0);
+        case 11: return Q(1);
+        case 12: return Q(2);
+        case 13: return P.p[3] ? __ldg(P.p[3] + i * P.stride[3]) : P.f_weight;      // weight
+        case 14: return P.f_mass;
+        case 15: return P.f_charge;
+        case 16: return P.f_time;
+        case 17: return P.f_mass / P.f_amu;                                        // mass_u
+        case 18: return P.f_charge / P.f_qe;                                       // charge_e
+        case 19: return X(0) * 1e6;                                                // x_um
+        case 20: return X(1) * 1e6;
+        case 21: return X(2) * 1e6;
+        case 46: { const double a = X(0), b = X(1); return sqrt(a * a + b * b); }  // r_xy
+        case 47: { const double a = X(1), b = X(2); return sqrt(a * a + b * b); }  // r_yz
+        case 48: { const double a = X(2), b = X(0); return sqrt(a * a + b * b); }  // r_zx
+        case 49: { const double a = X(0), b = X(1), c = X(2); return sqrt(a * a + b * b + c * c); }   // r_xyz
+        default: break;
+    }
+    const double px = Q(0), py = Q(1), pz = Q(2);
+    switch (kind) {
+        case 37: return atan2(sqrt(py * py + pz * pz), px);                        // angle_xaxis
+        case 38: return atan2(sqrt(pz * pz + px * px), py);
+        case 39: return atan2(sqrt(px * px + py * py), pz);
+        case 40: return atan2(py, px);                                             // angle_xy
+        case 41: return atan2(px, py);
+        case 42: return atan2(pz, py);
+        case 43: return atan2(py, pz);
+        case 44: return atan2(px, pz);
+        case 45: return atan2(pz, px);
+        default: break;
+    }
+    const double np2 = (px * px + py * py + pz * pz) / P.f_mc2;                    // _np2
+    const double gm1 = np2 / (sqrt(1.0 + np2) + 1.0);                              // gamma_m1
+    const double gamma = gm1 + 1.0;
+    const double ekin = gm1 * P.f_mass * P.f_c2;
+    const double mass_u = P.f_mass / P.f_amu, charge_e = P.f_charge / P.f_qe;
+    switch (kind) {
+        case 22: return np2;
+        case 23: return gamma * P.f_mass;                                          // gamma_m
+        case 24: return sqrt(gm1 * gm1 + 2.0 * gm1) / (gm1 + 1.0);                 // beta
+        case 25: return sqrt(gm1 * gm1 + 2.0 * gm1) / (gm1 + 1.0) * P.f_c;         // v
+        case 26: return px / (gamma * P.f_mass);                                   // vx
+        case 27: return py / (gamma * P.f_mass);
+        case 28: return pz / (gamma * P.f_mass);
+        case 29: return px / (gamma * P.f_mass) / P.f_c;                           // betax
+        case 30: return py / (gamma * P.f_mass) / P.f_c;
+        case 31: return pz / (gamma * P.f_mass) / P.f_c;
+        case 32: return P.f_mass * P.f_c2;                                         // Eruhe
+        case 33: return ekin / P.f_qe / 1e6 / mass_u;                              // Ekin_MeV_amu
+        case 34: return ekin / P.f_qe / 1e6 / mass_u * charge_e;                   // Ekin_MeV_qm
+        case 35: return ekin / P.f_qe / 1e3 / mass_u;                              // Ekin_keV_amu
+        case 36: return ekin / P.f_qe / 1e3 / mass_u * charge_e;                   // Ekin_keV_qm
+        default: return 0.0;
+    }
+}
+
+// Coordinate `a` of particle i: the array in slot a, or -- in the fused instances -- an axis expression.
+template <bool F>
+__device__ __forceinline__ double particle_coord(const DepositParams &P, int a, int64_t i) {
+    if (F && P.akind[a] != 0) return scalar_value(P, P.akind[a], i);
+    return ld_stream(P.p[a] + i * P.stride[a]);
+}
+// the same for kernels that are not templated on F (probe, sort keys): run-time check
+__device__ __forceinline__ double particle_coord_rt(const DepositParams &P, int a, int64_t i) {
+    if (P.akind[a] != 0) return scalar_value(P, P.akind[a], i);
+    return ld_stream(P.p[a] + i * P.stride[a]);
+}
+
+// Weight of particle i for the weighted kernels: the weights array (1 / the species' constant when absent), times
+// the fused scalar when one is requested.
 __device__ __forceinline__ double fused_factor(const DepositParams &P, int64_t i) {
-    return kinetic_value(P.fuse_kind, __ldg(P.q[0] + i * P.qstride[0]), __ldg(P.q[1] + i * P.qstride[1]),
-                         __ldg(P.q[2] + i * P.qstride[2]), P.f_mass, P.f_mc2, P.f_c2, P.f_qe);
+    return P.fuse_kind != 0 ? scalar_value(P, P.fuse_kind, i) : 1.0;
 }
 // F = false is the plain weighted kernel (the weights array exists); F = true instantiates the fused
 // variants, whose weights array is optional.  A template flag, not a run-time one: the fused code
@@ -216,8 +306,8 @@ __device__ __forceinline__ double fused_factor(const DepositParams &P, int64_t i
 template <bool F>
 __device__ __forceinline__ double particle_weight(const DepositParams &P, int64_t i) {
     if (!F) return ld_stream(P.p[3] + i * P.stride[3]);
-    const double w = P.p[3] ? ld_stream(P.p[3] + i * P.stride[3]) : 1.0;
-    return __dmul_rn(w, fused_factor(P, i));
+    const double w = P.p[3] ? ld_stream(P.p[3] + i * P.stride[3]) : P.f_weight;
+    return P.fuse_kind != 0 ? __dmul_rn(w, scalar_value(P, P.fuse_kind, i)) : w;
 }
 
 // Fire-and-forget fp64 reduction into global memory: a single native

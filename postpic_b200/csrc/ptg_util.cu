@@ -81,6 +81,20 @@ __global__ void __launch_bounds__(256) k_scale(double *g, int64_t count, double 
         g[i] = __dmul_rn(g[i], f);
 }
 
+// g[i] /= divisor with a true IEEE division: bit-identical to the reference's `h /= dV` (particles.py:1101-1102)
+__global__ void __launch_bounds__(256) k_divide(double *g, int64_t count, double dv) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += step) g[i] = __ddiv_rn(g[i], dv);
+}
+
+cudaError_t divide_f64(double *grid, int64_t count, double divisor, int sm_count, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    int64_t want = (count + 255) / 256;
+    int64_t cap = (int64_t)sm_count * 8;
+    k_divide<<<(int)(want < cap ? want : cap), 256, 0, st>>>(grid, count, divisor);
+    return cudaGetLastError();
+}
+
 cudaError_t scale_f64(double *grid, int64_t count, double factor, int sm_count, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     int64_t want = (count + 255) / 256;
@@ -124,6 +138,20 @@ cudaError_t weights_f64(int kind, int64_t n, const double *px, const double *py,
     k_weights<<<(int)(want < cap ? want : cap), 256, 0, st>>>(kind, n, px, py, pz, weight, strides ? strides[0] : 1,
                                                              strides ? strides[1] : 1, strides ? strides[2] : 1,
                                                              strides ? strides[3] : 1, mass, c, qe, out);
+    return cudaGetLastError();
+}
+
+// out[i] = scalar `kind` of particle i (the very device function the fused deposit kernels call)
+__global__ void __launch_bounds__(256) k_scalar(const DepositParams P, int kind, double *out) {
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += step) out[i] = scalar_value(P, kind, i);
+}
+
+cudaError_t scalar_f64(const DepositParams &P, int kind, double *out, int sm_count, cudaStream_t st) {
+    if (P.n <= 0) return cudaSuccess;
+    int64_t want = (P.n + 255) / 256;
+    int64_t cap = (int64_t)sm_count * 8;
+    k_scalar<<<(int)(want < cap ? want : cap), 256, 0, st>>>(P, kind, out);
     return cudaGetLastError();
 }
 

@@ -219,7 +219,122 @@ def scale_(grid, factor):
     return grid
 
 
+def divide_(grid, divisor):
+    """grid /= divisor in place on the device with a true IEEE division: the h /= dV of particles.py:1102, bit for bit."""
+    torch = _torch()
+    with torch.cuda.device(grid.device):
+        _lib.check(_lib.load().ptg_divide_f64(grid.data_ptr(), grid.numel(), float(divisor),
+                                              torch.cuda.current_stream().cuda_stream))
+    return grid
+
+
 WEIGHT_KINDS = {'gamma_m1': 1, 'gamma': 2, 'Ekin': 3, 'Ekin_MeV': 4, 'Ekin_keV': 5, 'p': 6}
+
+# postpic's default scalar context (scalarproperties.py:159-222) as the enumerated kinds PTG_S_* of ptg_b200.h
+SCALAR_KINDS = dict(WEIGHT_KINDS)
+SCALAR_KINDS.update({
+    'x': 7, 'y': 8, 'z': 9, 'px': 10, 'py': 11, 'pz': 12, 'weight': 13, 'w': 13, 'mass': 14, 'm': 14,
+    'charge': 15, 'q': 15, 'time': 16, 't': 16, 'mass_u': 17, 'm_u': 17, 'charge_e': 18, 'q_e': 18,
+    'x_um': 19, 'y_um': 20, 'z_um': 21, '_np2': 22, 'gamma_m': 23, 'beta': 24, 'v': 25, 'vx': 26, 'vy': 27,
+    'vz': 28, 'betax': 29, 'betay': 30, 'betaz': 31, 'Eruhe': 32, 'Ekin_MeV_amu': 33, 'Ekin_MeV_qm': 34,
+    'Ekin_keV_amu': 35, 'Ekin_keV_qm': 36, 'angle_xaxis': 37, 'angle_yaxis': 38, 'angle_zaxis': 39,
+    'angle_xy': 40, 'angle_yx': 41, 'angle_yz': 42, 'angle_zy': 43, 'angle_zx': 44, 'angle_xz': 45,
+    'r_xy': 46, 'r_yz': 47, 'r_zx': 48, 'r_xyz': 49})
+_NEEDS_POS = {7: 'x', 8: 'y', 9: 'z', 19: 'x', 20: 'y', 21: 'z', 46: 'xy', 47: 'yz', 48: 'zx', 49: 'xyz'}
+_NO_ARRAYS = (13, 14, 15, 16, 17, 18, 32)
+
+
+def scalar_arrays_needed(kind):
+    """Names of the atomic arrays scalar `kind` reads ('weight' is optional: a constant works too)."""
+    if kind in _NEEDS_POS:
+        return list(_NEEDS_POS[kind])
+    if kind in _NO_ARRAYS:
+        return []
+    return ['px', 'py', 'pz']
+
+
+def _species_args(species, n, device):
+    """ptg_deposit_args with the atomic arrays / constants of one species filled in.  `species`: dict with CUDA
+    tensors x, y, z, px, py, pz (those that exist), weight (tensor or number), mass, charge, time (numbers)."""
+    torch = _torch()
+    args = _lib.DepositArgs()
+    args.struct_size = ctypes.sizeof(_lib.DepositArgs)
+    args.n = n
+    keep = []
+
+    def arr(name):
+        t = species.get(name)
+        if t is None or not is_cuda_tensor(t):
+            return None, 1
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+            keep.append(t)
+        _check_tensor(t, name)
+        if t.numel() < n or t.device != device:
+            raise ValueError('{}: wrong length or device'.format(name))
+        return (t.data_ptr() if n else None), (t.stride(0) if n > 1 else 1)
+    pos = [arr(k) for k in 'xyz']
+    mom = [arr(k) for k in ('px', 'py', 'pz')]
+    args.pos_x, args.pos_y, args.pos_z = (p[0] for p in pos)
+    pstr = (ctypes.c_int64 * 3)(*[p[1] for p in pos])
+    args.pos_strides = ctypes.cast(pstr, ctypes.c_void_p)
+    args.px, args.py, args.pz = (p[0] for p in mom)
+    qstr = (ctypes.c_int64 * 3)(*[p[1] for p in mom])
+    args.pstrides = ctypes.cast(qstr, ctypes.c_void_p)
+    wt = species.get('weight', 1.0)
+    wptr, wstride = arr('weight')
+    args.w = wptr
+    args.weight_const = 1.0 if wptr is not None else float(wt)
+    sstr = (ctypes.c_int64 * 4)(1, 1, 1, wstride)
+    args.strides = ctypes.cast(sstr, ctypes.c_void_p)
+    args.mass = float(species.get('mass', 0.0) or 0.0)
+    args.charge = float(species.get('charge', 0.0) or 0.0)
+    args.time = float(species.get('time', 0.0) or 0.0)
+    args.c = float(species.get('c', 299792458.0))
+    args.elementary_charge = float(species.get('elementary_charge', 1.602176634e-19))
+    args.atomic_mass = float(species.get('atomic_mass', 1.66053906660e-27))
+    keep += [pstr, qstr, sstr]
+    return args, keep
+
+
+def scalar(name, species, n, device):
+    """The per-particle scalar `name` of postpic's default scalar context as a CUDA tensor, evaluated by the
+    library (ptg_scalar_f64: the device function the fused deposit kernels call)."""
+    torch = _torch()
+    args, keep = _species_args(species, n, device)
+    out = torch.empty(n, dtype=torch.float64, device=device)
+    with torch.cuda.device(device):
+        args.stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(_lib.load().ptg_scalar_f64(ctypes.byref(args), SCALAR_KINDS[name], out.data_ptr()))
+    return out
+
+
+def deposit_scalars_into(grid, plan, species, n, axes, weight_expr=None, method=None, zero=True, mask=None, stream=None):
+    """createField's inner step in ONE pass over a device-resident species: axis a of every particle is the scalar
+    `axes[a]`, its weight is weight * `weight_expr` (None: weight alone), both evaluated inside the deposit kernel
+    from the atomic arrays in `species` -- no N-sized temporary is written."""
+    torch = _torch()
+    if len(axes) != plan.ndim:
+        raise ValueError('expected {} axis scalars'.format(plan.ndim))
+    if grid.dtype != torch.float64 or not grid.is_contiguous() or grid.numel() != plan.cells:
+        raise ValueError('grid must be a contiguous float64 tensor of {} elements'.format(plan.cells))
+    args, keep = _species_args(species, n, grid.device)
+    args.ndim, args.shape = plan.ndim, plan.shape
+    for a, nm in enumerate(axes):
+        args.axis_kind[a] = SCALAR_KINDS[nm]
+    args.fuse_kind = SCALAR_KINDS[weight_expr] if weight_expr is not None else 0
+    args.lo, args.inv = plan.lo.ctypes.data, plan.inv.ctypes.data
+    args.bins = ctypes.cast(plan.cbins, ctypes.c_void_p)
+    args.grid = grid.data_ptr()
+    args.flags = _lib.METHODS[method] | (_lib.ZERO_GRID if zero else 0)
+    if mask is not None:
+        if mask.dtype not in (torch.bool, torch.uint8) or mask.dim() != 1 or mask.numel() < n or mask.device != grid.device:
+            raise ValueError('mask must be a 1-D bool / uint8 CUDA tensor with one entry per particle')
+        args.mask, args.mask_stride = (mask.data_ptr() if n else None), (mask.stride(0) if n > 1 else 1)
+    with torch.cuda.device(grid.device):
+        args.stream = torch.cuda.current_stream().cuda_stream if stream is None else stream
+        _lib.check(_lib.load().ptg_deposit_ex_f64(ctypes.byref(args)))
+    return grid
 
 
 def kinetic_weights(kind, px, py, pz, weight=None, mass=None, c=299792458.0, elementary_charge=1.602176634e-19):

@@ -11,9 +11,18 @@ small stand-ins here (`ArraySource`, `Field`, the scalar table) exist so the dis
 can be exercised and tested without postpic installed.  When postpic is installed, a
 maintainer swaps one import instead.
 
-Per-particle scalars are evaluated with numpy for host arrays and with torch ops for
-CUDA tensors, so a device-resident particle set never leaves HBM before deposition.
+The keyword handling and the empty-histogram branch of `_createHistgram` and the tail of
+`createField` follow the reference statement by statement (particles.py:1043-1095, :1150-1167):
+that is API-contract glue a drop-in must reproduce (same keywords, defaults, exceptions and
+names), not the hot path -- everything from the axis / weight evaluation down is this
+package's own.
+
+Per-particle scalars of device-resident species are evaluated INSIDE the deposit kernels when
+they are names of postpic's default scalar context (enumerated kinds, `device.SCALAR_KINDS`);
+arbitrary expression strings go through a small whitelisting evaluator (numpy for host arrays,
+torch ops for CUDA tensors).
 """
+import ast
 import warnings
 
 import numpy as np
@@ -96,6 +105,11 @@ def _findscalarattr(scalarf, attrib, default='unknown'):
     return default if ret is None else ret
 
 
+# scalar kinds (device.SCALAR_KINDS) that read the species' mass / charge as a constant
+_NEED_MASS = frozenset([1, 2, 3, 4, 5, 14, 17] + list(range(22, 37)))
+_NEED_CHARGE = frozenset([15, 18, 34, 36])
+
+
 class ArraySource(object):
     """One species worth of particles held as arrays (numpy, or torch CUDA tensors).
 
@@ -169,17 +183,48 @@ class ArraySource(object):
         return np.asarray(v, dtype=np.float64)
 
 
+_ALLOWED_NODES = (ast.Expression, ast.BinOp, ast.UnaryOp, ast.Compare, ast.BoolOp, ast.Call, ast.Name, ast.Load,
+                  ast.Constant, ast.Add, ast.Sub, ast.Mult, ast.Div, ast.Pow, ast.Mod, ast.FloorDiv, ast.USub, ast.UAdd,
+                  ast.Invert, ast.Not, ast.And, ast.Or, ast.BitAnd, ast.BitOr, ast.BitXor, ast.Eq, ast.NotEq, ast.Lt,
+                  ast.LtE, ast.Gt, ast.GtE)
+_code_cache = {}
+
+
+def _safe_eval(expr, ns, funcs):
+    """Evaluate an arithmetic expression string over the names in `ns`.  Like numexpr (which the reference uses,
+    particles.py:290-330) it accepts arithmetic, comparisons and calls of the known functions only: attribute
+    access, subscripts, lambdas, comprehensions ... are rejected before anything is evaluated."""
+    code = _code_cache.get(expr)
+    if code is None:
+        try:
+            tree = ast.parse(str(expr), mode='eval')
+        except SyntaxError as exc:
+            raise ValueError('cannot parse scalar expression {!r}: {}'.format(expr, exc))
+        for node in ast.walk(tree):
+            if not isinstance(node, _ALLOWED_NODES):
+                raise ValueError('scalar expression {!r}: {} is not allowed'.format(expr, type(node).__name__))
+            if isinstance(node, ast.Call) and not (isinstance(node.func, ast.Name) and node.func.id in funcs
+                                                   and not node.keywords):
+                raise ValueError('scalar expression {!r}: only calls of {} are allowed'.format(expr, sorted(funcs)))
+            if isinstance(node, ast.Constant) and not isinstance(node.value, (int, float, bool)):
+                raise ValueError('scalar expression {!r}: only numeric constants are allowed'.format(expr))
+        code = compile(tree, '<scalar>', 'eval')
+        _code_cache[expr] = code
+    return eval(code, {'__builtins__': {}}, ns)          # noqa: S307 (whitelisted AST)
+
+
 class _Namespace(dict):
     """Name resolution for `eval`: atomic arrays, derived scalars (recursively), constants."""
 
     def __init__(self, source, funcs):
         dict.__init__(self)
         self._source = source
+        self._funcs = funcs
         self.update(funcs)
 
     def __missing__(self, key):
         if key in _SCALARS:
-            val = eval(_SCALARS[key][0], {'__builtins__': {}}, self)      # noqa: S307 (own table)
+            val = _safe_eval(_SCALARS[key][0], self, self._funcs)
         else:
             try:
                 val = self._source.atomic(key)
@@ -370,7 +415,7 @@ class MultiSpecies(object):
             funcs = _torch_funcs() if s.device is not None else _numpy_funcs()
             ns = _Namespace(s, funcs)
             try:
-                val = eval(str(expr), {'__builtins__': {}}, ns)          # noqa: S307
+                val = _safe_eval(str(expr), ns, funcs)
             except NameError as exc:        # unknown scalar: the reference raises KeyError('"name" not found!')
                 raise KeyError('"{}" not found!'.format(getattr(exc, 'name', None) or str(exc)))
             if np.ndim(val) == 0 and not _device.is_cuda_tensor(val):
@@ -444,11 +489,18 @@ class MultiSpecies(object):
         on_device = bool(self._sources) and all(s.device is not None for s in self._sources)
         on_host = bool(self._sources) and all(s.device is None for s in self._sources)
         several = sum(1 for s in self._sources if len(s) > 0) > 1
+        if self._sources and not (on_device or on_host):
+            raise TypeError('a MultiSpecies must hold either host (numpy) species or CUDA-resident species, not both')
         try:
             if (on_device or (on_host and several)) and self.npart > 0:
                 data = None                       # evaluated per species below, nothing is concatenated
-                for sp in sps:                    # (unknown scalars must still raise here)
-                    MultiSpecies(self._sources[0])(sp)
+                for src in self._sources:         # (unknown scalars must still raise here -- or give the
+                    if len(src) == 0:             #  empty histogram under force=True -- for EVERY species)
+                        continue
+                    probe = MultiSpecies(ArraySource(src.species, {k: (v[:1] if (np.ndim(v) == 1 or _device.is_cuda_tensor(v)) else v)
+                                                                   for k, v in src._arrays.items()}))
+                    for sp in sps:
+                        probe(sp)
             else:
                 data = [self(sp) for sp in sps]
         except KeyError:
@@ -519,26 +571,77 @@ class MultiSpecies(object):
         h /= dV
         return h, edges
 
+    def _scalar_plan(self, src, sps, weights):
+        """(axis scalar names, weight expression name or None) when every axis and the extra weight of species
+        `src` is a NAMED scalar of the default context whose atomic arrays are CUDA tensors -- then the deposit
+        kernels evaluate them per particle themselves (device.deposit_scalars_into) and no N-sized temporary
+        exists; None when anything needs the generic evaluator."""
+        names = [getattr(sp, 'symbol', sp) for sp in sps]
+        wkey = getattr(weights, 'symbol', weights)
+        if wkey in ('1', 1, 1.0, None):
+            wkey = None
+        kinds = _device.SCALAR_KINDS
+        if not all(isinstance(nm, str) and nm in kinds for nm in names + ([wkey] if wkey is not None else [])):
+            return None
+        arrs = src._arrays
+        need = set()
+
+        def number(key):
+            v = arrs.get(key, None)
+            return v is not None and not _device.is_cuda_tensor(v) and np.ndim(v) == 0
+        for nm in names + ([wkey] if wkey is not None else []):
+            k = kinds[nm]
+            need.update(_device.scalar_arrays_needed(k))
+            if k in _NEED_MASS and not number('mass'):
+                return None                                   # per-particle or missing mass: generic evaluator
+            if k in _NEED_CHARGE and not number('charge'):
+                return None
+            if k == 16 and not number('time'):
+                return None
+        if not all(_device.is_cuda_tensor(arrs.get(k)) for k in need):
+            return None
+        wt = arrs.get('weight', 1.0)
+        if not (_device.is_cuda_tensor(wt) or np.ndim(wt) == 0):
+            return None
+        return names, wkey
+
+    def _species_dict(self, src):
+        c = _sc.c if _sc is not None else _CONSTANTS['c']
+        qe = _sc.elementary_charge if _sc is not None else _CONSTANTS['elementary_charge']
+        amu = _sc.atomic_mass if _sc is not None else _CONSTANTS['atomic_mass']
+        d = {k: v for k, v in src._arrays.items() if k in ('x', 'y', 'z', 'px', 'py', 'pz', 'weight', 'mass', 'charge', 'time')}
+        d.setdefault('weight', 1.0)
+        d.update(c=c, elementary_charge=qe, atomic_mass=amu)
+        return d
+
     def _createHistgram_per_species(self, sps, ranges, weights, bins, shape, keep_on_device=False):
         """Several device-resident species: deposition is linear in the particle set, so every
         species is deposited into the SAME device grid, one after the other, instead of first
-        concatenating all per-particle arrays (the np.hstack of particles.py:662-674).  The
-        1/dV scaling also happens on the device; only the finished grid crosses PCIe."""
+        concatenating all per-particle arrays (the np.hstack of particles.py:662-674).  Named scalars are
+        evaluated inside the deposit kernel (no N-sized temporaries); the 1/dV scaling also happens on the
+        device; only the finished grid crosses PCIe."""
         from .._setup import as_bins
         from ._routines import _DEFAULT_BINS
         torch = _device._torch()
         nd = len(sps)
-        singles = [MultiSpecies(s) for s in self._sources if len(s) > 0]
-        masks = [self._mask_of(m._sources[0]) for m in singles]
         dev = self._sources[0].device
         c = _sc.c if _sc is not None else _CONSTANTS['c']
         qe = _sc.elementary_charge if _sc is not None else _CONSTANTS['elementary_charge']
-        per = []            # (axis data, weights array or None, fused spec or None) per species
-        for m in singles:
+        per = []            # one job per species with at least one selected particle
+        for src in self._sources:
+            if len(src) == 0:
+                continue
+            m = MultiSpecies(src)
+            mk = self._mask_of(src)
+            if mk is not None and not bool(mk.any()):
+                continue                                   # nothing of this species passes the filter
+            plan_s = self._scalar_plan(src, sps, weights)
+            if plan_s is not None:
+                per.append(dict(kind='scalars', src=src, names=plan_s[0], wkey=plan_s[1], mask=mk))
+                continue
             d = [m(sp) for sp in sps]
             d = [a if _device.is_cuda_tensor(a) else torch.as_tensor(np.asarray(a, dtype='float64'), device=dev)
                  for a in d]
-            src = m._sources[0]
             kind = m._fusable(weights)
             if kind is not None:
                 # weight * <kinetic scalar> is evaluated inside the deposit kernels (ptg_deposit_fused_f64)
@@ -553,28 +656,44 @@ class MultiSpecies(object):
                              mass=float(src._arrays['mass']), c=c, elementary_charge=qe)
             else:
                 w, fused = m._weights(weights), None
-            per.append((d, w, fused))
-        per = [p + (mk,) for p, mk in zip(per, masks)]
+            per.append(dict(kind='arrays', d=d, w=w, fused=fused, mask=mk))
+        if bins is None:
+            bins = _DEFAULT_BINS[nd]
+        elif np.isscalar(bins):
+            bins = (bins,) * nd
+        if not per:                                        # every species filtered away: an all-zero histogram
+            h = np.zeros(tuple(as_bins(bins[0] if nd == 1 else bins, nd)))
+            edges = tuple(np.linspace(r[0], r[1], nb + 1) if r is not None and r[0] is not None and r[1] is not None
+                          else np.linspace(0, 1, nb + 1) for r, nb in zip(ranges[:nd], h.shape))
+            return h, edges
+
+        def axis_values(job, a):
+            if job['kind'] == 'arrays':
+                t = job['d'][a]
+            else:                                          # a temporary, only to complete a missing range end
+                t = _device.scalar(job['names'][a], self._species_dict(job['src']), len(job['src']), dev)
+            return t if job['mask'] is None else t[job['mask']]
         rng = []
         for a in range(nd):
             r = ranges[a]
             lo, hi = (None, None) if r is None else (r[0], r[1])
             if lo is None or hi is None:
-                mm = [_device.minmax(d[a] if mk is None else d[a][mk]) for d, _, _, mk in per]
-                lo = min(m[0] for m in mm) if lo is None else lo
-                hi = max(m[1] for m in mm) if hi is None else hi
+                mm = np.array([_device.minmax(axis_values(job, a)) for job in per])
+                lo = np.min(mm[:, 0]) if lo is None else lo        # np.min / np.max propagate NaN like the
+                hi = np.max(mm[:, 1]) if hi is None else hi        # reference's reduction over the hstack-ed data
             rng.append((lo, hi))
-        if bins is None:
-            bins = _DEFAULT_BINS[nd]
-        elif np.isscalar(bins):
-            bins = (bins,) * nd
         plan = _device.Plan(rng, as_bins(bins[0] if nd == 1 else bins, nd), 2 if shape is None else shape)
-        grid = torch.zeros(plan.dims, dtype=torch.float64, device=self._sources[0].device)
-        for d, w, fused, mk in per:
+        grid = torch.zeros(plan.dims, dtype=torch.float64, device=dev)
+        for job in per:
+            if job['kind'] == 'scalars':
+                _device.deposit_scalars_into(grid, plan, self._species_dict(job['src']), len(job['src']), job['names'],
+                                             weight_expr=job['wkey'], zero=False, mask=job['mask'])
+                continue
+            d, w = job['d'], job['w']
             _device.deposit_into(grid, plan, [t if t.dtype == torch.float64 else t.to(torch.float64) for t in d],
                                  w if (w is None or w.dtype == torch.float64) else w.to(torch.float64), zero=False,
-                                 fused=fused, mask=mk)
-        _device.scale_(grid, 1.0 / plan.cell_volume())
+                                 fused=job['fused'], mask=job['mask'])
+        _device.divide_(grid, plan.cell_volume())          # h /= dV, an IEEE division like the reference's
         if keep_on_device:
             return _DeviceGrid(grid, plan.interior), tuple(plan.edges)
         h = grid.cpu().numpy()[plan.interior]

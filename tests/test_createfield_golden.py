@@ -65,7 +65,7 @@ def test_createfield_matches_real_postpic_on_gpu(key, dims, sps, kw, cond, doubl
     _particlestogrid.method = None
     ms = _collection(dims, cond, doubled, device=("cuda:0" if resident == "device" else None))
     f = ms.createField(*sps, **{k: (list(v) if isinstance(v, list) else v) for k, v in kw.items()})
-    _check(key, f, ms, rtol=1e-11)
+    _check(key, f, ms, rtol=1e-12)
 
 
 # ---- row a5: the call forms of histogramdd against the real postpic's histogramdd ----
@@ -171,3 +171,76 @@ def test_field_and_axis_naming_rules(cpu_stack):
     assert [f.name, f.axes[0].name, f.axes[0].unit] == [str(v) for v in GOLDEN["naming_expr_axis"]]
     with pytest.raises(KeyError, match='"zzz" not found!'):
         ms.createField('x', 'zzz', bins=[4, 4])
+
+
+@pytest.mark.gpu
+def test_every_enumerated_scalar_kind_matches_real_postpic():
+    """ptg_scalar_f64 -- the device function the deposit kernels call for fused axis / weight expressions -- against
+    the per-particle values of the reference's scalar context on its dummy species, every available scalar."""
+    import torch
+    from postpic_b200 import ArraySource, MultiSpecies, device
+    src = ArraySource.dummy(SCALAR_N, dimensions=2, device='cuda')
+    sp = MultiSpecies(src)._species_dict(src)
+    checked = 0
+    for key, name, unit, available in GOLDEN["ctx_table"]:
+        key = str(key)
+        if available != '1' or key not in device.SCALAR_KINDS:
+            continue
+        ref = GOLDEN["ctx_" + key]
+        got = device.scalar(key, sp, len(src), torch.device('cuda', torch.cuda.current_device())).cpu().numpy()
+        scale = np.max(np.abs(ref))
+        tol = 4e-16 if key.startswith('angle') else 1e-15          # atan2: <= 2 ulp between libm and CUDA
+        assert np.max(np.abs(got - ref)) <= tol * scale, key
+        checked += 1
+    assert checked >= 40
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("axes,weights", [(('x_um', 'angle_xy'), 'gamma'), (('px', 'gamma'), None), (('r_xy',), 'Ekin_MeV'),
+                                          (('x', 'y'), 'beta'), (('vx', 'vy'), 'w'), (('angle_xaxis', 'p'), 'Ekin_keV')])
+def test_fused_axis_expressions_equal_eager_evaluation(axes, weights):
+    """createField on device-resident species with named scalars on the axes: the kernels evaluate them per particle
+    (no temporaries); the result must equal the deposit of the eagerly evaluated arrays, and the host (numpy) stack."""
+    import torch
+    from postpic_b200 import ArraySource, MultiSpecies, device
+    n = 300000
+    dsrc = ArraySource.dummy(n, dimensions=2, seed=3, device='cuda')
+    hsrc = ArraySource.dummy(n, dimensions=2, seed=3)
+    dms, hms = MultiSpecies(dsrc), MultiSpecies(hsrc)
+    assert dms._scalar_plan(dsrc, axes, weights if weights else '1') is not None
+    kw = dict(bins=[48, 40][:len(axes)], shape=2)
+    for a, nm in zip('xyz', axes):
+        v = np.asarray(hms(nm))
+        kw['range' + a] = (float(v.min()) - 0.01 * abs(float(v.min())) - 1e-30, float(v.max()) * 1.01 + 1e-30)
+    if weights:
+        kw['weights'] = weights
+    fd = dms.createField(*axes, **kw)
+    fh = hms.createField(*axes, **kw)
+    ref = np.asarray(fh.matrix)
+    assert np.max(np.abs(np.asarray(fd.matrix) - ref)) <= 1e-11 * np.max(np.abs(ref))
+    # with a filter (predicated deposition) and a range end taken from the data
+    kw.pop('rangex')
+    fd = dms.filter('gamma > 1.2').createField(*axes, **kw)
+    fh = hms.filter('gamma > 1.2').createField(*axes, **kw)
+    ref = np.asarray(fh.matrix)
+    assert np.allclose(fd.axes[0].grid_node, fh.axes[0].grid_node, rtol=1e-14, atol=0)
+    assert np.max(np.abs(np.asarray(fd.matrix) - ref)) <= 1e-11 * np.max(np.abs(ref))
+
+
+@pytest.mark.gpu
+def test_filtered_collection_with_an_empty_species_selection():
+    """electrons + 'ions' under a filter no ion passes, range ends from the data: the reference histograms
+    the concatenated compressed arrays without error; so must the per-species device path (and the host path)."""
+    from postpic_b200 import ArraySource, MultiSpecies
+    n = 20000
+    for dev in (None, 'cuda'):
+        e = ArraySource.dummy(n, dimensions=2, seed=1, device=dev)
+        ion = ArraySource.dummy(n // 2, dimensions=2, seed=2, device=dev)
+        for k in ('px', 'py', 'pz'):
+            ion._arrays[k] = ion._arrays[k] * 1e-6              # slow: gamma ~ 1
+        ion.species = 'ion'
+        ms = MultiSpecies(e, ion).filter('gamma > 1.5')
+        f = ms.createField('x', 'y', bins=[16, 12], shape=1)
+        only = MultiSpecies(e).filter('gamma > 1.5').createField('x', 'y', bins=[16, 12], shape=1)
+        assert np.allclose(np.asarray(f.matrix), np.asarray(only.matrix), rtol=1e-12, atol=0)
+        assert np.array_equal(f.axes[0].grid_node, only.axes[0].grid_node)
