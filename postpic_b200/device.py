@@ -357,6 +357,22 @@ def kinetic_weights(kind, px, py, pz, weight=None, mass=None, c=299792458.0, ele
     return out
 
 
+def upload_into(dst, offset, arr):
+    """dst[offset:offset+len(arr)] = arr for a host float64 array (any element stride, pageable or pinned) and a
+    contiguous float64 CUDA tensor `dst`, through the library's threaded pinned staging ring."""
+    a = np.asarray(arr, dtype=np.float64)
+    if a.ndim != 1:
+        raise ValueError('1-D array expected')
+    if a.size > 1 and a.strides[0] % 8:
+        a = np.ascontiguousarray(a)
+    if offset < 0 or offset + a.size > dst.numel() or not dst.is_contiguous():
+        raise ValueError('upload_into: destination range out of bounds')
+    if a.size:
+        _lib.check(_lib.load().ptg_upload_host_f64(a.size, a.ctypes.data, a.strides[0] // 8 if a.size > 1 else 1,
+                                                   dst.data_ptr() + 8 * int(offset), dst.device.index))
+    return dst
+
+
 def upload(arr, device_index=None):
     """Host float64 array (any stride, pageable or pinned) -> contiguous CUDA tensor through the library's
     threaded pinned staging ring (about 4x faster than torch's pageable copy)."""

@@ -169,6 +169,67 @@ class ArraySource(object):
         extent = {'x': (-2.0, 10.0), 'y': (-5.0, 5.0), 'z': (-4.0, 4.0)}
         return cls('electron', arrs, extent={k: extent[k] for k in 'xyz'[:dimensions]})
 
+    ATTRIBS = ('x', 'y', 'z', 'px', 'py', 'pz', 'weight', 'mass', 'charge', 'id')
+
+    @classmethod
+    def from_dumpreader(cls, reader, species, device=None, attribs=None, chunk=1 << 22):
+        """One species of a postpic dump reader (anything with the particle half of `Dumpreader_ifc`,
+        /root/reference/postpic/datareader/datareader.py:247-263: `getSpecies(species, attrib)` returning a
+        per-particle sequence, a single float for a per-species constant, or raising KeyError; optionally
+        `time()`, `simextent(axis)`, `simdimensions()`) as an ArraySource.
+
+        Every attribute is pulled on its own and -- with `device` -- goes chunk by chunk (`chunk` particles at a
+        time) through the library's pinned staging ring straight into its device array: whatever the reader hands
+        out (float32, integer ids, strided views, lazily read HDF5 / SDF datasets that only materialise the slice
+        asked for) is converted to float64 one chunk at a time, so no full-size host copy of the species is ever
+        made, and nothing is concatenated (the reference: _SingleSpecies.__getitem__ particles.py:128-150 reads
+        whole arrays, MultiSpecies.__call_sp :662-674 hstacks them).  Attributes the dump lacks are skipped."""
+        arrs = {}
+        n = None
+        dev = None
+        if device is not None:
+            torch = _device._torch()
+            dev = torch.device(device)
+            if dev.index is None:
+                dev = torch.device('cuda', torch.cuda.current_device())
+        for name in (attribs or cls.ATTRIBS):
+            try:
+                val = reader.getSpecies(species, name)
+            except KeyError:
+                continue
+            if np.ndim(val) == 0 and not hasattr(val, '__len__'):
+                arrs[name] = float(val)                  # per-species constant (mass, charge, a uniform weight)
+                continue
+            m = len(val)
+            if n is None:
+                n = m
+            elif m != n:
+                raise ValueError('attribute {!r} of species {!r} has {} entries, expected {}'.format(name, species, m, n))
+            if dev is None:
+                arrs[name] = np.asarray(val, dtype=np.float64)
+                continue
+            out = _device._torch().empty(m, dtype=_device._torch().float64, device=dev)
+            for i0 in range(0, m, int(chunk)):
+                _device.upload_into(out, i0, np.asarray(val[i0:i0 + int(chunk)], dtype=np.float64))
+            arrs[name] = out
+        if n is None:
+            raise KeyError('species {!r} has no per-particle attribute'.format(species))
+        arrs.setdefault('weight', 1.0)
+        if hasattr(reader, 'time'):
+            try:
+                arrs['time'] = float(reader.time())
+            except Exception:
+                pass
+        extent = {}
+        if hasattr(reader, 'simextent'):
+            for ax in 'xyz':
+                try:
+                    e = reader.simextent(ax)
+                    extent[ax] = (float(e[0]), float(e[1]))
+                except Exception:
+                    pass
+        return cls(species, arrs, extent=extent)
+
     def atomic(self, name):
         if name not in self._arrays:
             raise KeyError(name)
