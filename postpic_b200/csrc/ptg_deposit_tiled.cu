@@ -198,19 +198,40 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
         if (!s_last) return;
         __threadfence();
     }
+    // the last CTA's first warp gathers the 16 partial records in parallel (one lane per probe CTA, all fields of a
+    // record in flight at once) and reduces them with shuffles: a serial loop over volatile loads cost 15 us
+    if (threadIdx.x >= 32) return;
     double mad_sum[3] = {0, 0, 0};
     int blocks_used = 0;
     long long eq_pairs = 0, all_pairs = 0, near_pairs = 0;
     double wmax = 0.0;
-    for (int blk = 0; blk < (int)gridDim.x; ++blk) {
-        const volatile TileConfig::Part *q = &cfg->part[blk];
-        wmax = fmax(wmax, q->wmax);
-        if (q->cnt < 32) continue;
-        ++blocks_used;
-        for (int a = 0; a < ND; ++a) mad_sum[a] += q->mad[a];
-        eq_pairs += q->eq_pairs;
-        all_pairs += q->all_pairs;
-        near_pairs += q->near_pairs;
+    {
+        const int l = threadIdx.x;
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f;
+        int cnt = 0, eq = 0, al = 0, ne = 0;
+        double wm = 0.0;
+        if (l < (int)gridDim.x) {
+            const TileConfig::Part *q = &cfg->part[l];
+            cnt = __ldcg(&q->cnt);
+            m0 = __ldcg(&q->mad[0]); m1 = __ldcg(&q->mad[1]); m2 = __ldcg(&q->mad[2]);
+            eq = __ldcg(&q->eq_pairs); al = __ldcg(&q->all_pairs); ne = __ldcg(&q->near_pairs);
+            wm = __ldcg(&q->wmax);
+        }
+        const bool used = cnt >= 32;
+        double v[3] = {used ? (double)m0 : 0.0, used ? (double)m1 : 0.0, used ? (double)m2 : 0.0};
+        int bu = used ? 1 : 0, e1 = used ? eq : 0, a1 = used ? al : 0, n1 = used ? ne : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) v[a] += __shfl_xor_sync(0xffffffffu, v[a], o);
+            bu += __shfl_xor_sync(0xffffffffu, bu, o);
+            e1 += __shfl_xor_sync(0xffffffffu, e1, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+            wm = fmax(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+        }
+        for (int a = 0; a < 3; ++a) mad_sum[a] = v[a];
+        blocks_used = bu; eq_pairs = e1; all_pairs = a1; near_pairs = n1; wmax = wm;
     }
     if (threadIdx.x != 0) return;
     struct { int mode; int ext[3]; float est_hit; float run_frac; float near_frac; } c;
@@ -232,7 +253,8 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
         double ext[3] = {need[0], need[1], need[2]};
         if (prod > kTileCells) {
             // shrink all axes by a common factor, never below the stencil width
-            const double f = pow((double)kTileCells / prod, 1.0 / ND);
+            const double ratio = (double)kTileCells / prod;
+            const double f = ND == 1 ? ratio : ND == 2 ? sqrt(ratio) : cbrt(ratio);
             for (int a = 0; a < ND; ++a) { ext[a] = floor(need[a] * f); if (ext[a] < NW + 1) ext[a] = NW + 1; }
         }
         for (int a = 0; a < ND; ++a) c.ext[a] = (int)ext[a] < P.dims[a] ? (int)ext[a] : P.dims[a];
@@ -793,7 +815,7 @@ __global__ void __launch_bounds__((FxThreads<ND, S>::value), 1) k_deposit_tile_f
 // replicas into the global grid at the end.  This is the path of postpic's 1-D energy spectra.
 constexpr int kST = 1024;     // threads per CTA, one CTA per SM
 constexpr int kSU = 4;        // particles in flight per thread
-constexpr int kSCheck = 4;    // fixed point: main-loop iterations between two range checks
+constexpr int kSCheck = 8;    // fixed point: main-loop iterations between two range checks
 
 template <int ND, int S, bool W, bool F, bool FX>
 __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P, const TileConfig *gate) {

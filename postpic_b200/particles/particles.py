@@ -197,7 +197,7 @@ class ArraySource(object):
                 val = reader.getSpecies(species, name)
             except KeyError:
                 continue
-            if np.ndim(val) == 0 and not hasattr(val, '__len__'):
+            if not hasattr(val, '__len__'):                 # (never np.ndim(val): that would materialise a lazy dataset)
                 arrs[name] = float(val)                  # per-species constant (mass, charge, a uniform weight)
                 continue
             m = len(val)

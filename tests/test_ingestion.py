@@ -71,7 +71,7 @@ class LazyColumn(object):
 
     def __getitem__(self, sl):
         out = self._a[sl]
-        self.largest = max(self.largest, len(out))
+        self.largest = max(self.largest, len(out) if np.ndim(out) else 1)
         return out
 
 
@@ -125,3 +125,12 @@ def test_from_dumpreader_streams_chunks_into_device_arrays():
     ref = np.asarray(fh.matrix)
     assert fd.device_matrix is not None
     assert np.max(np.abs(np.asarray(fd.matrix) - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def test_from_dumpreader_accepts_awkward_attribute_types_on_host():
+    from postpic_b200 import ArraySource
+    rd = AwkwardReader(4000)
+    a = ArraySource.from_dumpreader(rd, 'electron')
+    assert a.atomic('x').dtype == np.float64 and np.array_equal(a.atomic('x'), rd._d['x'].astype(np.float64))
+    assert np.array_equal(a.atomic('px'), np.ascontiguousarray(rd._d['px']))
+    assert np.array_equal(a.atomic('weight'), rd.lazy._a)
