@@ -348,6 +348,8 @@ def launches_per_step(method, nd, shape, n, plan):
         return 1 + 1 + 1 + (1 if wide else 0) + rows
     if method in ("tiled", "tiled_exact"):
         return 2
+    if method == "fixed":
+        return 6                      # max|w|, probe, quantum, tile kernel, direct kernel, finish
     if method == "sorted":
         passes = -(-max(plan.cells.bit_length(), 1) // 8)
         return 2 + 4 * passes + 2 * nw ** nd   # keys, offsets, 4 sort kernels per 8-bit pass, two reduce launches per colour
@@ -684,7 +686,9 @@ def run_b200_arm(args):
                  ("cfg4 weights precomputed (5e8)", "cfg4", int(5e8), "random", "auto", None, False, 3, None),
                  ("cfg4 weight * Ekin_MeV fused (2e8)", "cfg4", int(2e8), "random", "auto", None, True, 3, None),
                  ("cfg5 AUTO (1e9)", "cfg5", int(1e9), "random", "auto", None, False, 3, None),
-                 ("cfg5 deterministic SORTED (2e8)", "cfg5", int(2e8), "random", "sorted", None, False, 2, "reproducible")]
+                 ("cfg5 deterministic SORTED (2e8)", "cfg5", int(2e8), "random", "sorted", None, False, 2, "reproducible"),
+                 ("cfg5 deterministic FIXED: integer accumulation (1e9)", "cfg5", int(1e9), "random", "fixed", None, False, 3, "reproducible"),
+                 ("cfg2 deterministic FIXED: integer accumulation (1e8)", "cfg2", int(1e8), "random", "fixed", None, False, 5, "reproducible")]
         for tag, nm, nn, order, meth, shp, fz, st, extra in plan_:
             try:
                 configs.append(measure_config(tag, nm, nn, order, meth, dev, peak, shape=shp, fused=fz, steps=st, extra=extra))

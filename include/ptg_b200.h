@@ -72,6 +72,12 @@ extern "C" {
                                        runs alive when neighbours' base cells differ by one (odd
                                        shapes on cell-ordered input); (S+2)^ndim <= 27 only        */
 
+#define PTG_METHOD_FIXED     0x70u  /* deterministic AND order-independent: every contribution is rounded once to a
+                                       multiple of 2^-45 of the power of two above the exact largest |weight| and all
+                                       sums are integer sums (64-bit in shared memory, 128-bit per cell in global
+                                       memory); bit-identical across runs, launch geometries and input permutations,
+                                       at the speed of the atomic paths                                           */
+
 /* Shared-memory tiles (method TILED, also when AUTO picks it) accumulate in 64-bit fixed point on native
  * 32-bit shared atomics: each contribution is rounded to a multiple of 2^-45 of the power of two above the
  * largest sampled |weight| (<= 2^-46 relative rounding per contribution; integer-valued weights below 2^45

@@ -25,10 +25,11 @@ METHOD_TILED = 0x30
 METHOD_SORTED = 0x40
 METHOD_RUNS = 0x50
 METHOD_RUNS_WIDE = 0x60
+METHOD_FIXED = 0x70
 EXACT_ACCUM = 0x100        # keep shared-memory tiles in fp64 (CAS loops) instead of 64-bit fixed point
 METHODS = {None: METHOD_AUTO, 'auto': METHOD_AUTO, 'global': METHOD_GLOBAL, 'rows': METHOD_ROWS,
            'tiled': METHOD_TILED, 'sorted': METHOD_SORTED, 'runs': METHOD_RUNS, 'runs_wide': METHOD_RUNS_WIDE,
-           'tiled_exact': METHOD_TILED | EXACT_ACCUM, 'auto_exact': METHOD_AUTO | EXACT_ACCUM}
+           'fixed': METHOD_FIXED, 'tiled_exact': METHOD_TILED | EXACT_ACCUM, 'auto_exact': METHOD_AUTO | EXACT_ACCUM}
 
 
 class PtgError(RuntimeError):

@@ -303,6 +303,14 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
             }
             break;
         }
+        case PTG_METHOD_FIXED: {
+            if (n <= 0) break;
+            ptg::TileConfig *cfg;
+            int rc = next_tile_config(d, &cfg);
+            if (rc) return rc;
+            PTG_CUDA(ptg::deposit_fixed(ndim, shape, P, cfg, d->sm_count, st));
+            break;
+        }
         case PTG_METHOD_RUNS:
             PTG_CUDA(ptg::deposit_runs(ndim, shape, P, nullptr, false, d->sm_count, st));
             break;
@@ -725,7 +733,7 @@ int host_pipeline(int ndim, int shape, int64_t n, const double *x, const double 
     const double *src[4] = {x, ndim >= 2 ? y : nullptr, ndim >= 3 ? z : nullptr, w};
     const unsigned dflags = flags & ~PTG_ZERO_GRID;
     // the deterministic method must add the chunks to the grid in a fixed order: one stream
-    const bool ordered = (flags & PTG_METHOD_MASK) == PTG_METHOD_SORTED;
+    const bool ordered = (flags & PTG_METHOD_MASK) == PTG_METHOD_SORTED || (flags & PTG_METHOD_MASK) == PTG_METHOD_FIXED;
     int slot = 0;
     const int64_t chunk = direct ? kChunk : kStageChunk;
     bool slot_used[kSlots] = {};

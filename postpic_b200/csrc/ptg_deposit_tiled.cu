@@ -324,12 +324,14 @@ __device__ __forceinline__ void flush_tile(double *tile, const Window &wd, const
     // merge the tile (all its replicas) into the global grid, coalesced along the last axis, and clear it
     for (int c = threadIdx.x; c < cells; c += TT) {
         double v;
+        long long kq = 0;
         if constexpr (FX) {
             // replicas are summed as integers (exact), one conversion and one multiply by the quantum (a power of two)
             unsigned *lo = reinterpret_cast<unsigned *>(tile);
             long long k = fx_take(lo, c);
             for (int r = 1; r < replicas; ++r) k += fx_take(lo, r * cells + c);
             v = __dmul_rn(__ll2double_rn(k), fx_q);
+            kq = k;
         } else {
             v = tile[c];
             tile[c] = 0.0;
@@ -347,7 +349,8 @@ __device__ __forceinline__ void flush_tile(double *tile, const Window &wd, const
                 const int iy = r / wd.e[2], iz = r - iy * wd.e[2];
                 lin = ((int64_t)(wd.o[0] + ix) * P.dims[1] + wd.o[1] + iy) * P.dims[2] + wd.o[2] + iz;
             }
-            red_add(P.grid + lin, v);
+            if (FX && P.fixed_lo != nullptr) fixed_accumulate(P, lin, kq);   // method FIXED: stay integer
+            else red_add(P.grid + lin, v);
         }
     }
 }
@@ -587,7 +590,11 @@ __device__ __forceinline__ double pick_w(const double (&wl)[NW], int j) {
 // particle, lane j of a group takes cell j of every stencil row along the last axis (the pattern of k_deposit_quads);
 // the products keep the reference's operation order.
 template <int ND, int S, bool W>
-__device__ __forceinline__ void drain_rows(const DepositParams &P, const double *q, int count, int lane) {
+__device__ __forceinline__ void drain_rows(const DepositParams &P, const double *q, int count, int lane, double inv_q) {
+    auto put = [&](double *cell, double v) {
+        if (P.fixed_lo != nullptr) fixed_add(P, cell - P.grid, v, inv_q);
+        else red_add(cell, v);
+    };
     constexpr int NW = StencilWidth<S>::value;
     const int g = lane >> 2, j = lane & 3;
     if (g >= count || j >= NW) return;
@@ -599,13 +606,13 @@ __device__ __forceinline__ void drain_rows(const DepositParams &P, const double 
     const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
     double *cell = P.grid + ((int64_t)b[0] * g1 + b[1]) * g2 + b[2] + j;
     if (ND == 1) {
-        red_add(cell, W ? __dmul_rn(pick_w<NW>(wx, j), w) : pick_w<NW>(wx, j));
+        put(cell, W ? __dmul_rn(pick_w<NW>(wx, j), w) : pick_w<NW>(wx, j));
     } else if (ND == 2) {
         const double wl = pick_w<NW>(wy, j);
 #pragma unroll
         for (int a = 0; a < NW; ++a) {
             const double c = __dmul_rn(wx[a], wl);
-            red_add(cell + a * g1, W ? __dmul_rn(c, w) : c);
+            put(cell + a * g1, W ? __dmul_rn(c, w) : c);
         }
     } else {
         const double wl = pick_w<NW>(wz, j);
@@ -614,7 +621,7 @@ __device__ __forceinline__ void drain_rows(const DepositParams &P, const double 
 #pragma unroll
             for (int c2 = 0; c2 < NW; ++c2) {
                 const double c = __dmul_rn(__dmul_rn(wx[a], wy[c2]), wl);
-                red_add(cell + (a * g1 + c2) * g2, W ? __dmul_rn(c, w) : c);
+                put(cell + (a * g1 + c2) * g2, W ? __dmul_rn(c, w) : c);
             }
     }
 }
@@ -754,18 +761,21 @@ __global__ void __launch_bounds__((FxThreads<ND, S>::value), 1) k_deposit_tile_f
                 __syncwarp();
                 if (qcount >= 8) {
                     qcount -= 8;
-                    drain_rows<ND, S, W>(P, wq + qcount * 4, 8, lane);
+                    drain_rows<ND, S, W>(P, wq + qcount * 4, 8, lane, fx_inv_q);
                     __syncwarp();
                 }
             } else if (direct) {
-                double *g = P.grid + ((int64_t)b[0] * g1 + b[1]) * g2 + b[2];
+                const int64_t lin0 = ((int64_t)b[0] * g1 + b[1]) * g2 + b[2];
 #pragma unroll
                 for (int a = 0; a < NA; ++a)
 #pragma unroll
                     for (int c = 0; c < NC; ++c)
 #pragma unroll
-                        for (int d = 0; d < NDD; ++d)
-                            red_add(g + (a * g1 + c) * g2 + d, stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w));
+                        for (int d = 0; d < NDD; ++d) {
+                            const double v = stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w);
+                            if (P.fixed_lo != nullptr) fixed_add(P, lin0 + (a * g1 + c) * g2 + d, v, fx_inv_q);
+                            else red_add(P.grid + lin0 + (a * g1 + c) * g2 + d, v);
+                        }
             }
         }
         if (++since_eval == EV && more) {
@@ -801,7 +811,7 @@ __global__ void __launch_bounds__((FxThreads<ND, S>::value), 1) k_deposit_tile_f
             }
         }
     }
-    if (QUEUE && qcount > 0) drain_rows<ND, S, W>(P, wq, qcount, lane);
+    if (QUEUE && qcount > 0) drain_rows<ND, S, W>(P, wq, qcount, lane, fx_inv_q);
     __syncthreads();
     flush_tile<ND, TT, true>(tile, wd, P, cells, 1, fx_q);
 }
@@ -863,8 +873,11 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
 #pragma unroll
                     for (int c = 0; c < NC; ++c)
 #pragma unroll
-                        for (int d = 0; d < NDD; ++d)
-                            red_add(P.grid + off + (a * p1 + c) * p2 + d, stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w));
+                        for (int d = 0; d < NDD; ++d) {
+                            const double v = stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w);
+                            if (P.fixed_lo != nullptr) fixed_add(P, off + (a * p1 + c) * p2 + d, v, fx_inv_q);
+                            else red_add(P.grid + off + (a * p1 + c) * p2 + d, v);
+                        }
                 return;
             }
             fx_sum = __dadd_rn(fx_sum, W ? fabs(w) : 1.0);
@@ -891,6 +904,10 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
             } else if (FXA) {
                 long long k = fx_take(ctile, c);
                 for (int r = 1; r < replicas; ++r) k += fx_take(ctile, r * cells + c);
+                if (P.fixed_lo != nullptr) {             // method FIXED: stay integer
+                    if (k != 0) fixed_accumulate(P, c, k);
+                    continue;
+                }
                 v = __dmul_rn(__ll2double_rn(k), fx_q);
             } else {
                 v = tile[c];
@@ -940,7 +957,8 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
 // launchers
 // ---------------------------------------------------------------------------------
 template <int ND, int S, bool W, bool FX>
-static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int force, int sm_count, cudaStream_t st) {
+static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int force, int sm_count, cudaStream_t st,
+                                const FixedState *fixed) {
     constexpr int NW = StencilWidth<S>::value;
     constexpr int TT = TileThreads<(ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW)>::value;
     const bool fuse = W && fused_mode(P);
@@ -950,6 +968,7 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k_probe<ND, S><<<kProbeBlocks, kTT, 0, st>>>(P, cfg, force, runs_wide_available(ND, S) ? 1 : 0, FX ? 0 : 1);
+    if (fixed != nullptr) fixed_set_scale(cfg, fixed, st);      // method FIXED: the quantum comes from the exact max |w|
     if ((int64_t)P.dims[0] * P.dims[1] * P.dims[2] <= kTileCells) {
         // the whole padded grid fits the tile: lean kernel without window management
         auto small = fuse ? k_deposit_small<ND, S, W, W, FX> : k_deposit_small<ND, S, W, false, FX>;
@@ -972,29 +991,31 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
 }
 
 template <int ND, int S>
-static cudaError_t tiled_w(const DepositParams &P, TileConfig *cfg, int force, bool exact, int sm, cudaStream_t st) {
+static cudaError_t tiled_w(const DepositParams &P, TileConfig *cfg, int force, bool exact, int sm, cudaStream_t st,
+                           const FixedState *fixed) {
     const bool w = P.p[3] || fused_mode(P);
-    if (exact) return w ? launch_tiled<ND, S, true, false>(P, cfg, force, sm, st) : launch_tiled<ND, S, false, false>(P, cfg, force, sm, st);
-    return w ? launch_tiled<ND, S, true, true>(P, cfg, force, sm, st) : launch_tiled<ND, S, false, true>(P, cfg, force, sm, st);
+    if (exact) return w ? launch_tiled<ND, S, true, false>(P, cfg, force, sm, st, nullptr) : launch_tiled<ND, S, false, false>(P, cfg, force, sm, st, nullptr);
+    return w ? launch_tiled<ND, S, true, true>(P, cfg, force, sm, st, fixed) : launch_tiled<ND, S, false, true>(P, cfg, force, sm, st, fixed);
 }
 
 template <int ND>
-static cudaError_t tiled_s(int shape, const DepositParams &P, TileConfig *cfg, int force, bool exact, int sm, cudaStream_t st) {
+static cudaError_t tiled_s(int shape, const DepositParams &P, TileConfig *cfg, int force, bool exact, int sm, cudaStream_t st,
+                           const FixedState *fixed) {
     switch (shape) {
-        case 0: return tiled_w<ND, 0>(P, cfg, force, exact, sm, st);
-        case 1: return tiled_w<ND, 1>(P, cfg, force, exact, sm, st);
-        case 2: return tiled_w<ND, 2>(P, cfg, force, exact, sm, st);
-        default: return tiled_w<ND, 3>(P, cfg, force, exact, sm, st);
+        case 0: return tiled_w<ND, 0>(P, cfg, force, exact, sm, st, fixed);
+        case 1: return tiled_w<ND, 1>(P, cfg, force, exact, sm, st, fixed);
+        case 2: return tiled_w<ND, 2>(P, cfg, force, exact, sm, st, fixed);
+        default: return tiled_w<ND, 3>(P, cfg, force, exact, sm, st, fixed);
     }
 }
 
 cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, bool exact,
-                          int sm_count, cudaStream_t st) {
+                          int sm_count, cudaStream_t st, const FixedState *fixed) {
     if (P.n <= 0) return cudaSuccess;
     switch (ndim) {
-        case 1: return tiled_s<1>(shape, P, cfg, force, exact, sm_count, st);
-        case 2: return tiled_s<2>(shape, P, cfg, force, exact, sm_count, st);
-        default: return tiled_s<3>(shape, P, cfg, force, exact, sm_count, st);
+        case 1: return tiled_s<1>(shape, P, cfg, force, exact, sm_count, st, fixed);
+        case 2: return tiled_s<2>(shape, P, cfg, force, exact, sm_count, st, fixed);
+        default: return tiled_s<3>(shape, P, cfg, force, exact, sm_count, st, fixed);
     }
 }
 

@@ -38,9 +38,18 @@ cudaError_t deposit_global(int ndim, int shape, const DepositParams &P, bool row
                            int sm_count, cudaStream_t st);
 
 // ptg_deposit_tiled.cu -- probe + tiled kernel; `force` ignores the probe's verdict
-// `exact`: accumulate the tile in fp64 (CAS loops) instead of 64-bit fixed point
+// ptg_deposit_fixed.cu -- method FIXED: deterministic, order-independent integer accumulation
+struct FixedState {
+    unsigned long long wmax_bits;      // bit pattern of the largest finite |weight| (non-negative doubles order like integers)
+    unsigned long long pad;
+};
+void fixed_set_scale(TileConfig *cfg, const FixedState *state, cudaStream_t st);   // cfg->fx_* := quantum from the exact max
+cudaError_t deposit_fixed(int ndim, int shape, const DepositParams &P, TileConfig *cfg, int sm_count, cudaStream_t st);
+
+// `exact`: accumulate the tile in fp64 (CAS loops) instead of 64-bit fixed point; `fixed` (method FIXED only): the
+// probe's sampled quantum is replaced by the one derived from the exact maximum weight
 cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, bool exact,
-                          int sm_count, cudaStream_t st);
+                          int sm_count, cudaStream_t st, const FixedState *fixed = nullptr);
 
 // ptg_deposit_runs.cu -- run-length accumulation in registers for cell-ordered input
 // (`wide`: the variant whose register window is one cell wider per axis, mode kModeRunsWide)

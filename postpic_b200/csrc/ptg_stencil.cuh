@@ -134,6 +134,11 @@ struct DepositParams {
     int64_t pos_stride[3];
     double f_mass, f_mc2, f_c2, f_qe;   // mass, (mass*c)^2, c^2, elementary charge
     double f_c, f_charge, f_time, f_amu, f_weight;   // c, species charge, dump time, atomic mass unit, constant macro weight
+    // method FIXED (deterministic): every contribution is added as an integer number of quanta to a 128-bit
+    // accumulator per cell (low / high 64-bit words); null = the ordinary fp64 grid is the target
+    unsigned long long *fixed_lo;
+    long long *fixed_hi;
+    int fixed_split;        // representation of the accumulators, see fixed_accumulate()
 };
 
 // the kernels' fused (F = true) instances do the work when a weight or an axis expression is evaluated in the kernel
@@ -314,6 +319,33 @@ __device__ __forceinline__ double particle_weight(const DepositParams &P, int64_
 // RED.E.ADD.F64.RN.STRONG.GPU, resolved by the L2 atomic units.
 __device__ __forceinline__ void red_add(double *addr, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
+// Integer accumulation in global memory, two 64-bit words per cell, in one of two representations:
+//   split (fixed_split = 1, the default): value = hi * 2^31 + lo.  A contribution k is added as its low 31 bits to
+//     `lo` and k >> 31 (arithmetic) to `hi` with two fire-and-forget reductions (RED.E.ADD.64, no return trip).
+//     `lo` takes 2^33 contributions per cell before it could wrap; the host selects this form when n * cells-per-
+//     particle stays below that.
+//   carry (fixed_split = 0): value = hi * 2^64 + lo, a true 128-bit sum: the returning add on the low word tells
+//     whether it wrapped, the high word gets the carry / sign extension.  No limit, ~2x slower (return trips).
+// Integer addition is associative and commutative: the sums do not depend on the order of the atomics.
+__device__ __forceinline__ void fixed_accumulate(const DepositParams &P, int64_t lin, long long k) {
+    if (P.fixed_split) {
+        atomicAdd(P.fixed_lo + lin, (unsigned long long)(k & 0x7fffffffll));
+        const long long h = k >> 31;
+        if (h != 0) atomicAdd(reinterpret_cast<unsigned long long *>(P.fixed_hi + lin), (unsigned long long)h);
+    } else {
+        const unsigned long long a = (unsigned long long)k;
+        const unsigned long long old = atomicAdd(P.fixed_lo + lin, a);
+        const long long h = (k < 0 ? -1ll : 0ll) + ((old + a) < old ? 1ll : 0ll);
+        if (h != 0) atomicAdd(reinterpret_cast<unsigned long long *>(P.fixed_hi + lin), (unsigned long long)h);
+    }
+}
+// one contribution for method FIXED: finite values as quanta, NaN / inf straight into the fp64 grid (they poison the
+// cell whatever the order)
+__device__ __forceinline__ void fixed_add(const DepositParams &P, int64_t lin, double v, double inv_q) {
+    if (fabs(v) <= 1.79769313486231570e308) fixed_accumulate(P, lin, __double2ll_rn(__dmul_rn(v, inv_q)));
+    else red_add(P.grid + lin, v);
 }
 
 }  // namespace ptg

@@ -26,7 +26,7 @@ CONFIGS = {
     "cfg5": (2, 2, (1024, 1024), ((0.0, 1.0), (0.0, 1.0))),
 }
 ORDERS = ("random", "xsorted", "cellsorted")
-METHODS = (None, "rows", "tiled", "runs", "runs_wide", "global", "sorted")
+METHODS = (None, "rows", "tiled", "runs", "runs_wide", "global", "sorted", "fixed")
 
 _cache = {}
 
@@ -141,7 +141,7 @@ def test_baseline_geometry_shape0_integer_weights_bit_exact(oracle, name, order)
     ref = oracle_padded(oracle, name, coords, w, shape=0)
     dc = [torch.from_numpy(c).cuda() for c in coords]
     dw = torch.from_numpy(w).cuda()
-    for m in (None, "global", "tiled", "runs", "runs_wide", "sorted"):
+    for m in (None, "global", "tiled", "runs", "runs_wide", "sorted", "fixed"):
         grid, _ = device.deposit(dc, dw, range=ranges, bins=bins, shape=0, method=m)
         assert np.array_equal(grid.cpu().numpy(), ref), "%s/%s/%s" % (name, order, m)
     # and plain counting (weights=None)

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "ptg_golden.npz"))
 ALL = [(nd, s, w) for nd in (1, 2, 3) for s in (0, 1, 2, 3) for w in (False, True)]
-METHODS = [None, 'global', 'rows', 'tiled', 'tiled_exact', 'sorted', 'runs', 'runs_wide']
+METHODS = [None, 'global', 'rows', 'tiled', 'tiled_exact', 'sorted', 'fixed', 'runs', 'runs_wide']
 
 
 def _skip_unavailable(method, nd, shape):
