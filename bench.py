@@ -424,6 +424,27 @@ def measure_config(tag, name, n, order, method, dev, peak, shape=None, fused=Fal
     if fz is None:
         tot = float(w.sum())
         out["mass_rel_err"] = abs(float(grid.sum()) - tot) / tot
+    if extra == "graph":
+        # a launch-bound call: the same call captured in a CUDA graph (20 calls per replay) shows the device-side cost
+        try:
+            gph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                ptgdev.deposit_into(grid, plan, coords, w, method=m, zero=True)
+            torch.cuda.current_stream().wait_stream(side)
+            with torch.cuda.graph(gph):
+                for _ in range(20):
+                    ptgdev.deposit_into(grid, plan, coords, w, method=m, zero=True)
+            ms_g = device_time(gph.replay, 20) / 20
+            out["us_per_call_python_loop"] = ms * 1e3
+            out["us_per_call_cuda_graph"] = ms_g * 1e3
+            out["value_cuda_graph"] = n / ms_g * 1e-6
+            tot = float(w.sum())
+            out["mass_rel_err_graph"] = abs(float(grid.sum()) - tot) / tot
+            del gph
+        except Exception as exc:                                   # pragma: no cover
+            out["cuda_graph_error"] = str(exc)[:160]
     if extra == "reproducible":
         # bit-reproducibility across 3 runs of the deterministic method
         ref = grid.clone()
@@ -673,7 +694,7 @@ def run_b200_arm(args):
     if world == 1 and not args.no_configs and args.order == "random" and name == "cfg2":
         # every BASELINE.json configuration and every particle shape at full single-GPU size (a few steps each)
         configs = []
-        plan_ = [("cfg1 as named (1e6 particles: launch bound, us per call matters)", "cfg1", int(1e6), "random", "auto", None, False, 200, None),
+        plan_ = [("cfg1 as named (1e6 particles: launch bound, us per call matters)", "cfg1", int(1e6), "random", "auto", None, False, 200, "graph"),
                  ("cfg1 at 1e8 particles", "cfg1", int(1e8), "random", "auto", None, False, 5, None),
                  ("cfg2 shape 0 (NGP)", "cfg2", int(1e8), "random", "auto", 0, False, 5, None),
                  ("cfg2 shape 1 (CIC)", "cfg2", int(1e8), "random", "auto", 1, False, 5, None),

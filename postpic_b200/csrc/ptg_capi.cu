@@ -268,9 +268,17 @@ int deposit_device(DeviceState *d, int ndim, int shape, int64_t n, const double 
             P.pos_stride[a] = fuse->pos_stride[a];
         }
     }
+    unsigned method = flags & PTG_METHOD_MASK;
+    if (method == PTG_METHOD_AUTO && !(flags & PTG_EXACT_ACCUM) && ptg::oneshot_applies(P, d->sm_count)) {
+        // small call on a small grid: everything (clearing the grid included) in one launch
+        ptg::TileConfig *cfg;
+        int rc = next_tile_config(d, &cfg);
+        if (rc) return rc;
+        PTG_CUDA(ptg::deposit_oneshot(ndim, shape, P, cfg, (flags & PTG_ZERO_GRID) != 0, d->sm_count, st));
+        return PTG_OK;
+    }
     if (flags & PTG_ZERO_GRID)
         PTG_CUDA(cudaMemsetAsync(grid, 0, (size_t)ptg_padded_cells(ndim, shape, bins) * sizeof(double), st));
-    unsigned method = flags & PTG_METHOD_MASK;
     if (method == PTG_METHOD_AUTO && n < (int64_t(1) << 21)) {
         // small calls are bound by launch latency, not by the GPU: skip the probe and the gated
         // launches.  A grid that fits the shared-memory tile is privatised, anything else goes

@@ -954,6 +954,160 @@ __global__ void __launch_bounds__(kST, 1) k_deposit_small(const DepositParams P,
 }
 
 // ---------------------------------------------------------------------------------
+// small calls in ONE launch (postpic's 1-D spectra of 1e5..1e6 particles: BASELINE cfg1 as named)
+// ---------------------------------------------------------------------------------
+// A call of a million particles is 2 us of HBM time; memset + probe + deposit kernel + their launch gaps made it
+// 30 us.  This kernel needs nothing before or after it: every CTA finds the largest |weight| of ITS particles (the
+// quantum of its own fixed-point tile), deposits them into shared memory, writes its tile to a scratch slab as doubles,
+// and the last CTA to finish (ticket) sums the slabs in CTA order and STORES the grid (or adds to it when the caller
+// did not ask for a cleared grid) -- no memset, no probe, no global atomics, and a result that is bit-reproducible.
+constexpr int kOneShotCells = 4096;
+constexpr int kOT = 1024;
+
+template <int ND, int S, bool W, bool F>
+__global__ void __launch_bounds__(kOT, 1) k_deposit_oneshot(const DepositParams P, double *scratch, unsigned *ticket,
+                                                            int zero_first) {
+    extern __shared__ double tile[];
+    __shared__ long long red_scratch[34];
+    __shared__ bool s_last;
+    constexpr int NW = StencilWidth<S>::value;
+    constexpr int NA = NW, NC = ND >= 2 ? NW : 1, NDD = ND >= 3 ? NW : 1;
+    const int cells = P.dims[0] * P.dims[1] * P.dims[2];
+    int replicas = kOneShotCells / cells;
+    replicas = replicas > 8 ? 8 : (replicas < 1 ? 1 : replicas);
+    unsigned *lo = reinterpret_cast<unsigned *>(tile);             // [replicas * cells] low words, then high words
+    unsigned *hi = lo + kOneShotCells;
+    double *extra = tile + kOneShotCells;                          // NaN / inf contributions, fp64
+    for (int c = threadIdx.x; c < kOneShotCells; c += kOT) { lo[c] = 0u; hi[c] = 0u; extra[c] = 0.0; }
+    const int64_t step = (int64_t)gridDim.x * kOT;
+    const int64_t first = (int64_t)blockIdx.x * kOT + threadIdx.x;
+    // pass 1: this CTA's largest finite |weight|  (the particles are re-read from L2 / L1 in pass 2)
+    double wmax = W ? 0.0 : 1.0;
+    if (W) {
+        for (int64_t i = first; i < P.n; i += step) {
+            if (!particle_selected(P, i)) continue;
+            const double a = fabs(particle_weight<F>(P, i));
+            if (a <= 1.79769313486231570e308) wmax = fmax(wmax, a);
+        }
+        wmax = block_max(wmax, red_scratch);
+    } else {
+        __syncthreads();
+    }
+    int e = wmax > 0.0 ? ilogb(wmax) + 1 : 0;
+    e = e < -960 ? -960 : (e > 960 ? 960 : e);
+    // a CTA sees at most 2^14 particles (the launcher guarantees it): |contribution| <= 4 |w| < 2^(e+2) leaves room for a
+    // quantum of 2^(e-47) in the 64-bit cells -- 4x finer than the windowed tile's
+    const double q = scalbn(1.0, e - 47), inv_q = scalbn(1.0, 47 - e);
+    unsigned *mylo = lo + ((threadIdx.x >> 5) % replicas) * cells;
+    const int p1 = ND >= 2 ? P.dims[1] : 1, p2 = ND >= 3 ? P.dims[2] : 1;
+    // pass 2: deposit
+    for (int64_t i = first; i < P.n; i += step) {
+        if (!particle_selected(P, i)) continue;
+        const double x = particle_coord<F>(P, 0, i);
+        const double y = ND >= 2 ? particle_coord<F>(P, 1, i) : 0.0;
+        const double z = ND >= 3 ? particle_coord<F>(P, 2, i) : 0.0;
+        const double w = W ? particle_weight<F>(P, i) : 1.0;
+        int b[3];
+        double wx[NW], wy[NW], wz[NW];
+        if (!particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz)) continue;
+        const int off = (b[0] * p1 + b[1]) * p2 + b[2];
+        const bool finite = !W || fabs(w) <= 1.79769313486231570e308;
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+#pragma unroll
+                for (int d = 0; d < NDD; ++d) {
+                    const double v = stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w);
+                    const int cell = off + (a * p1 + c) * p2 + d;
+                    if (finite) {
+                        const long long k = __double2ll_rn(__dmul_rn(v, inv_q));
+                        const unsigned l = (unsigned)k, h = (unsigned)((unsigned long long)k >> 32);
+                        const unsigned old = atomicAdd(mylo + cell, l);
+                        atomicAdd(mylo + kOneShotCells + cell, h + ((old + l) < old ? 1u : 0u));
+                    } else {
+                        atomicAdd(extra + cell, v);
+                    }
+                }
+    }
+    __syncthreads();
+    // this CTA's tile -> its scratch slab, as doubles
+    double *slab = scratch + (size_t)blockIdx.x * cells;
+    for (int c = threadIdx.x; c < cells; c += kOT) {
+        long long k = 0;
+        for (int r = 0; r < replicas; ++r)
+            k += (long long)(((unsigned long long)hi[r * cells + c] << 32) | lo[r * cells + c]);
+        slab[c] = __dadd_rn(__dmul_rn(__ll2double_rn(k), q), extra[c]);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int c = threadIdx.x; c < cells; c += kOT) {
+        double v = 0.0;
+        for (unsigned blk = 0; blk < gridDim.x; ++blk) v = __dadd_rn(v, __ldcg(scratch + (size_t)blk * cells + c));
+        if (zero_first) P.grid[c] = v;
+        else if (v != 0.0) red_add(P.grid + c, v);      // other streams (the host pipeline's chunks) may be adding too
+    }
+    if (threadIdx.x == 0) *ticket = 0u;               // the ring entry is ready for its next user
+}
+
+template <int ND, int S, bool W>
+static cudaError_t launch_oneshot(const DepositParams &P, TileConfig *cfg, bool zero_first, int sm_count, cudaStream_t st) {
+    const int cells = P.dims[0] * P.dims[1] * P.dims[2];
+    int64_t want = (P.n + 2047) / 2048;
+    const int blocks = (int)(want < sm_count ? (want < 1 ? 1 : want) : sm_count);
+    void *scratch = nullptr;
+    cudaError_t e = scratch_alloc(&scratch, (size_t)blocks * cells * sizeof(double), st);
+    if (e != cudaSuccess) return e;
+    const size_t smem = (size_t)kOneShotCells * 2 * sizeof(double);
+    const bool fuse = W && fused_mode(P);
+    auto kern = fuse ? k_deposit_oneshot<ND, S, W, W> : k_deposit_oneshot<ND, S, W, false>;
+    static bool opted_in[2][64] = {};                        // per device and instance: > 48 KB of dynamic shared memory
+    int dev = 0;
+    e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && (dev < 0 || dev >= 64 || !opted_in[fuse ? 1 : 0][dev])) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess && dev >= 0 && dev < 64) opted_in[fuse ? 1 : 0][dev] = true;
+    }
+    if (e == cudaSuccess) {
+        kern<<<blocks, kOT, smem, st>>>(P, static_cast<double *>(scratch), &cfg->ticket, zero_first ? 1 : 0);
+        e = cudaGetLastError();
+    }
+    cudaError_t e2 = cudaFreeAsync(scratch, st);
+    return e != cudaSuccess ? e : e2;
+}
+
+template <int ND>
+static cudaError_t oneshot_s(int shape, const DepositParams &P, TileConfig *cfg, bool zf, int sm, cudaStream_t st) {
+    const bool w = P.p[3] || fused_mode(P);
+    switch (shape) {
+        case 0: return w ? launch_oneshot<ND, 0, true>(P, cfg, zf, sm, st) : launch_oneshot<ND, 0, false>(P, cfg, zf, sm, st);
+        case 1: return w ? launch_oneshot<ND, 1, true>(P, cfg, zf, sm, st) : launch_oneshot<ND, 1, false>(P, cfg, zf, sm, st);
+        case 2: return w ? launch_oneshot<ND, 2, true>(P, cfg, zf, sm, st) : launch_oneshot<ND, 2, false>(P, cfg, zf, sm, st);
+        default: return w ? launch_oneshot<ND, 3, true>(P, cfg, zf, sm, st) : launch_oneshot<ND, 3, false>(P, cfg, zf, sm, st);
+    }
+}
+
+// (calls of a few thousand particles keep the path without a sample, which adds every contribution in fp64: a single
+// particle is then deposited bit for bit like the reference does)
+bool oneshot_applies(const DepositParams &P, int sm_count) {
+    return P.n >= 4096 && P.n < (int64_t(1) << 21) && P.n <= (int64_t)sm_count * 16384 &&
+           (int64_t)P.dims[0] * P.dims[1] * P.dims[2] <= kOneShotCells;
+}
+
+cudaError_t deposit_oneshot(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool zero_first, int sm_count,
+                            cudaStream_t st) {
+    switch (ndim) {
+        case 1: return oneshot_s<1>(shape, P, cfg, zero_first, sm_count, st);
+        case 2: return oneshot_s<2>(shape, P, cfg, zero_first, sm_count, st);
+        default: return oneshot_s<3>(shape, P, cfg, zero_first, sm_count, st);
+    }
+}
+
+// ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
 template <int ND, int S, bool W, bool FX>

@@ -51,6 +51,11 @@ cudaError_t deposit_fixed(int ndim, int shape, const DepositParams &P, TileConfi
 cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, bool exact,
                           int sm_count, cudaStream_t st, const FixedState *fixed = nullptr);
 
+// one launch for small calls on small grids (no memset, no probe); `zero_first`: the grid is overwritten, not added to
+bool oneshot_applies(const DepositParams &P, int sm_count);
+cudaError_t deposit_oneshot(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool zero_first, int sm_count,
+                            cudaStream_t st);
+
 // ptg_deposit_runs.cu -- run-length accumulation in registers for cell-ordered input
 // (`wide`: the variant whose register window is one cell wider per axis, mode kModeRunsWide)
 cudaError_t deposit_runs(int ndim, int shape, const DepositParams &P, const TileConfig *gate, bool wide, int sm_count,
