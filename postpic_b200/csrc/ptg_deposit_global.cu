@@ -290,6 +290,12 @@ __global__ void __launch_bounds__(256) k_merge_staggered(const DepositParams P, 
     }
 }
 
+__global__ void __launch_bounds__(256) k_zero_gated(double4 *p, int64_t n32, const TileConfig *gate) {
+    if (gate->mode != kModeRows) return;
+    const int64_t step = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32; i += step) p[i] = make_double4(0.0, 0.0, 0.0, 0.0);
+}
+
 // ---------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------
@@ -412,7 +418,14 @@ cudaError_t deposit_global(int ndim, int shape, const DepositParams &P0, bool ro
             void *buf = nullptr;
             cudaError_t e = scratch_alloc(&buf, bytes, st);           // stream-ordered, pooled: no sync
             if (e != cudaSuccess) return e;
-            e = cudaMemsetAsync(buf, 0, bytes, st);
+            if (gate != nullptr) {
+                // AUTO: clear the staging grid only if method ROWS is the one that runs (a 17 MB memset on the
+                // critical path of every AUTO call otherwise, and 17 MB of zeros pushed through the L2)
+                k_zero_gated<<<sm_count * 4, 256, 0, st>>>(static_cast<double4 *>(buf), (int64_t)(bytes / 32), gate);
+                e = cudaGetLastError();
+            } else {
+                e = cudaMemsetAsync(buf, 0, bytes, st);
+            }
             if (e != cudaSuccess) return e;
             P.stag = static_cast<double *>(buf);
             P.stag_pitch = pitch;

@@ -214,9 +214,22 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
                 for (int a = 0; a < ND; ++a) fits = fits && (unsigned)(b[a] - ab[a]) <= (unsigned)WD;
                 if (!fits) {                 // rare on cell-ordered input: close the run, open a new one
                     if (cur >= 0) commit(cur, acc);
-                    cur = (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2];      // dims beyond ndim are 1
 #pragma unroll
                     for (int a = 0; a < 3; ++a) ab[a] = b[a];
+                    if (WD && (S & 1)) {
+                        // Odd shapes: the base cell is the NEAREST node, f or f + 1 for a particle of floor cell f.
+                        // Anchor the widened window at the floor cell, not at this particle's base: every particle of
+                        // the cell then fits (offset 0 or 1 on each axis) and the run ends at the cell boundary --
+                        // anchored at the first particle's base, a later particle on the lower side would close it
+                        // (measured on cell-ordered cfg2: CIC 107 -> see profiles/r02/perf_runs_wide_anchor.log).
+                        const double c3[3] = {x[j], ND >= 2 ? y[j] : 0.0, ND >= 3 ? z[j] : 0.0};
+#pragma unroll
+                        for (int a = 0; a < ND; ++a) {
+                            const double u = scaled(c3[a], P.lo[a], P.inv[a]);
+                            if (u > 0.0 && __double2int_rz(__dadd_rn(u, 0.5)) > __double2int_rz(u)) ab[a] -= 1;
+                        }
+                    }
+                    cur = (ab[0] * P.dims[1] + ab[1]) * P.dims[2] + ab[2];      // dims beyond ndim are 1
 #pragma unroll
                     for (int k = 0; k < MV; ++k) acc[k] = 0.0;
                 }

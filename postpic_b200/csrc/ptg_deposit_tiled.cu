@@ -83,6 +83,34 @@ __device__ __forceinline__ long long block_sum(long long v, long long *scratch /
     return scratch[32];
 }
 
+// block-wide sums of N long longs at once (all threads get the results): one pass through shared memory instead of N
+template <int N>
+__device__ __forceinline__ void block_sum_n(long long (&v)[N], long long *scratch /* >= 32 * N + N */) {
+#pragma unroll
+    for (int k = 0; k < N; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) scratch[k * 32 + warp] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            long long t = lane < nwarp ? scratch[k * 32 + lane] : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) scratch[32 * N + k] = t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = scratch[32 * N + k];
+}
+
 // block-wide maximum of a non-negative double (all threads get the result)
 __device__ __forceinline__ double block_max(double v, long long *scratch /* >= 33 */) {
 #pragma unroll
@@ -138,6 +166,7 @@ __device__ __forceinline__ bool base_cells(const DepositParams &P, double x, dou
 template <int ND, int S>
 __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig *cfg, int force, int wide_ok, int exact) {
     __shared__ long long scratch[34];
+    __shared__ long long big_scratch[32 * 7 + 7];
     __shared__ bool s_last;
     constexpr int NW = StencilWidth<S>::value;
     // one probe CTA per block of kTT consecutive particles; the last CTA to finish decides
@@ -163,29 +192,31 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
                 if (!(aw <= 1.79769313486231570e308)) aw = 0.0;
             }
             part.wmax = block_max(aw, scratch);
-            const long long cnt = block_sum(ok ? 1 : 0, scratch);
+            // every count and sum of the sample in ONE block reduction, the deviations in a second one
+            // (27 barriers less than one reduction per quantity: the probe is on the critical path of every AUTO call)
+            const int key = ok ? (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2] : -1;
+            const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+            const bool pair = (threadIdx.x & 31) != 0 && key >= 0 && prev >= 0;   // pairs inside a warp only
+            // neighbours that a register window one cell wider per axis would still hold
+            // (either particle of the pair may be the one further along)
+            bool near = pair;
+            for (int a = 0; a < ND; ++a) {
+                const int pb = __shfl_up_sync(0xffffffffu, b[a], 1);
+                near = near && (b[a] - pb) >= -1 && (b[a] - pb) <= 1;
+            }
+            long long r1[7] = {ok ? 1 : 0, pair && key == prev ? 1 : 0, pair ? 1 : 0, near ? 1 : 0,
+                               ok ? b[0] : 0, ok ? b[1] : 0, ok ? b[2] : 0};
+            block_sum_n<7>(r1, big_scratch);
+            const long long cnt = r1[0];
             if (cnt >= 32) {
                 part.cnt = (int)cnt;
-                // consecutive particles with the same base cell (pairs inside a warp only)
-                const int key = ok ? (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2] : -1;
-                const int prev = __shfl_up_sync(0xffffffffu, key, 1);
-                const bool pair = (threadIdx.x & 31) != 0 && key >= 0 && prev >= 0;
-                part.eq_pairs = (int)block_sum(pair && key == prev ? 1 : 0, scratch);
-                part.all_pairs = (int)block_sum(pair ? 1 : 0, scratch);
-                // neighbours that a register window one cell wider per axis would still hold
-                // (either particle of the pair may be the one further along)
-                bool near = pair;
-                for (int a = 0; a < ND; ++a) {
-                    const int pb = __shfl_up_sync(0xffffffffu, b[a], 1);
-                    near = near && (b[a] - pb) >= -1 && (b[a] - pb) <= 1;
-                }
-                part.near_pairs = (int)block_sum(near ? 1 : 0, scratch);
-                for (int a = 0; a < ND; ++a) {
-                    const long long sum = block_sum(ok ? b[a] : 0, scratch);
-                    const long long mean = sum / cnt;
-                    const long long dev = block_sum(ok ? llabs((long long)b[a] - mean) : 0, scratch);
-                    part.mad[a] = (float)((double)dev / (double)cnt);
-                }
+                part.eq_pairs = (int)r1[1];
+                part.all_pairs = (int)r1[2];
+                part.near_pairs = (int)r1[3];
+                long long r2[3];
+                for (int a = 0; a < 3; ++a) r2[a] = ok ? llabs((long long)b[a] - r1[4 + a] / cnt) : 0;
+                block_sum_n<3>(r2, big_scratch);
+                for (int a = 0; a < ND; ++a) part.mad[a] = (float)((double)r2[a] / (double)cnt);
             }
         }
         if (threadIdx.x == 0) {
@@ -1112,7 +1143,7 @@ cudaError_t deposit_oneshot(int ndim, int shape, const DepositParams &P, TileCon
 // ---------------------------------------------------------------------------------
 template <int ND, int S, bool W, bool FX>
 static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int force, int sm_count, cudaStream_t st,
-                                const FixedState *fixed) {
+                                const FixedState *fixed, cudaEvent_t after_probe) {
     constexpr int NW = StencilWidth<S>::value;
     constexpr int TT = TileThreads<(ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW)>::value;
     const bool fuse = W && fused_mode(P);
@@ -1123,6 +1154,10 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
     if (e != cudaSuccess) return e;
     k_probe<ND, S><<<kProbeBlocks, kTT, 0, st>>>(P, cfg, force, runs_wide_available(ND, S) ? 1 : 0, FX ? 0 : 1);
     if (fixed != nullptr) fixed_set_scale(cfg, fixed, st);      // method FIXED: the quantum comes from the exact max |w|
+    if (after_probe != nullptr) {
+        e = cudaEventRecord(after_probe, st);
+        if (e != cudaSuccess) return e;
+    }
     if ((int64_t)P.dims[0] * P.dims[1] * P.dims[2] <= kTileCells) {
         // the whole padded grid fits the tile: lean kernel without window management
         auto small = fuse ? k_deposit_small<ND, S, W, W, FX> : k_deposit_small<ND, S, W, false, FX>;
@@ -1146,30 +1181,30 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
 
 template <int ND, int S>
 static cudaError_t tiled_w(const DepositParams &P, TileConfig *cfg, int force, bool exact, int sm, cudaStream_t st,
-                           const FixedState *fixed) {
+                           const FixedState *fixed, cudaEvent_t ev) {
     const bool w = P.p[3] || fused_mode(P);
-    if (exact) return w ? launch_tiled<ND, S, true, false>(P, cfg, force, sm, st, nullptr) : launch_tiled<ND, S, false, false>(P, cfg, force, sm, st, nullptr);
-    return w ? launch_tiled<ND, S, true, true>(P, cfg, force, sm, st, fixed) : launch_tiled<ND, S, false, true>(P, cfg, force, sm, st, fixed);
+    if (exact) return w ? launch_tiled<ND, S, true, false>(P, cfg, force, sm, st, nullptr, ev) : launch_tiled<ND, S, false, false>(P, cfg, force, sm, st, nullptr, ev);
+    return w ? launch_tiled<ND, S, true, true>(P, cfg, force, sm, st, fixed, ev) : launch_tiled<ND, S, false, true>(P, cfg, force, sm, st, fixed, ev);
 }
 
 template <int ND>
 static cudaError_t tiled_s(int shape, const DepositParams &P, TileConfig *cfg, int force, bool exact, int sm, cudaStream_t st,
-                           const FixedState *fixed) {
+                           const FixedState *fixed, cudaEvent_t ev) {
     switch (shape) {
-        case 0: return tiled_w<ND, 0>(P, cfg, force, exact, sm, st, fixed);
-        case 1: return tiled_w<ND, 1>(P, cfg, force, exact, sm, st, fixed);
-        case 2: return tiled_w<ND, 2>(P, cfg, force, exact, sm, st, fixed);
-        default: return tiled_w<ND, 3>(P, cfg, force, exact, sm, st, fixed);
+        case 0: return tiled_w<ND, 0>(P, cfg, force, exact, sm, st, fixed, ev);
+        case 1: return tiled_w<ND, 1>(P, cfg, force, exact, sm, st, fixed, ev);
+        case 2: return tiled_w<ND, 2>(P, cfg, force, exact, sm, st, fixed, ev);
+        default: return tiled_w<ND, 3>(P, cfg, force, exact, sm, st, fixed, ev);
     }
 }
 
 cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, bool exact,
-                          int sm_count, cudaStream_t st, const FixedState *fixed) {
+                          int sm_count, cudaStream_t st, const FixedState *fixed, cudaEvent_t after_probe) {
     if (P.n <= 0) return cudaSuccess;
     switch (ndim) {
-        case 1: return tiled_s<1>(shape, P, cfg, force, exact, sm_count, st, fixed);
-        case 2: return tiled_s<2>(shape, P, cfg, force, exact, sm_count, st, fixed);
-        default: return tiled_s<3>(shape, P, cfg, force, exact, sm_count, st, fixed);
+        case 1: return tiled_s<1>(shape, P, cfg, force, exact, sm_count, st, fixed, after_probe);
+        case 2: return tiled_s<2>(shape, P, cfg, force, exact, sm_count, st, fixed, after_probe);
+        default: return tiled_s<3>(shape, P, cfg, force, exact, sm_count, st, fixed, after_probe);
     }
 }
 

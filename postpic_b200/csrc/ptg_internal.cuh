@@ -48,8 +48,10 @@ cudaError_t deposit_fixed(int ndim, int shape, const DepositParams &P, TileConfi
 
 // `exact`: accumulate the tile in fp64 (CAS loops) instead of 64-bit fixed point; `fixed` (method FIXED only): the
 // probe's sampled quantum is replaced by the one derived from the exact maximum weight
+// `after_probe` (nullable): an event recorded right behind the probe kernel, before the tile kernel is launched
 cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, bool exact,
-                          int sm_count, cudaStream_t st, const FixedState *fixed = nullptr);
+                          int sm_count, cudaStream_t st, const FixedState *fixed = nullptr,
+                          cudaEvent_t after_probe = nullptr);
 
 // one launch for small calls on small grids (no memset, no probe); `zero_first`: the grid is overwritten, not added to
 bool oneshot_applies(const DepositParams &P, int sm_count);
