@@ -1077,8 +1077,20 @@ __global__ void __launch_bounds__(kOT, 1) k_deposit_oneshot(const DepositParams 
     if (!s_last) return;
     __threadfence();
     for (int c = threadIdx.x; c < cells; c += kOT) {
-        double v = 0.0;
-        for (unsigned blk = 0; blk < gridDim.x; ++blk) v = __dadd_rn(v, __ldcg(scratch + (size_t)blk * cells + c));
+        // slabs are summed in a fixed order (eight interleaved partial sums, then those): reproducible, and eight loads
+        // in flight per thread instead of a chain of 148 dependent L2 round trips
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned blk = 0;
+        for (; blk + 8 <= gridDim.x; blk += 8) {
+            double t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[k] = __ldcg(scratch + (size_t)(blk + k) * cells + c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = __dadd_rn(acc[k], t[k]);
+        }
+        for (; blk < gridDim.x; ++blk) acc[blk & 7] = __dadd_rn(acc[blk & 7], __ldcg(scratch + (size_t)blk * cells + c));
+        const double v = __dadd_rn(__dadd_rn(__dadd_rn(acc[0], acc[1]), __dadd_rn(acc[2], acc[3])),
+                                   __dadd_rn(__dadd_rn(acc[4], acc[5]), __dadd_rn(acc[6], acc[7])));
         if (zero_first) P.grid[c] = v;
         else if (v != 0.0) red_add(P.grid + c, v);      // other streams (the host pipeline's chunks) may be adding too
     }
