@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
     int blocks_used = 0;
     long long eq_pairs = 0, all_pairs = 0, near_pairs = 0;
     double wmax = 0.0;
+    int runs_blocks = 0, near_blocks = 0;
     {
         const int l = threadIdx.x;
         float m0 = 0.f, m1 = 0.f, m2 = 0.f;
@@ -249,6 +250,10 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
             wm = __ldcg(&q->wmax);
         }
         const bool used = cnt >= 32;
+        // blocks that are ordered in themselves: a dump that is ordered only in parts must not be sent to RUNS on the
+        // strength of the average
+        runs_blocks = __popc(__ballot_sync(0xffffffffu, used && al > 0 && eq * 2 >= al));
+        near_blocks = __popc(__ballot_sync(0xffffffffu, used && al > 0 && ne * 4 >= 3 * al));
         double v[3] = {used ? (double)m0 : 0.0, used ? (double)m1 : 0.0, used ? (double)m2 : 0.0};
         int bu = used ? 1 : 0, e1 = used ? eq : 0, a1 = used ? al : 0, n1 = used ? ne : 0;
 #pragma unroll
@@ -320,8 +325,9 @@ __global__ void __launch_bounds__(kTT) k_probe(const DepositParams P, TileConfig
     }
     // long runs of equal base cells: register run-length accumulation beats the tile
     // (break-even is an average run of ~2.5 particles)
-    if (!force && c.run_frac >= 0.6f) c.mode = kModeRuns;
-    else if (!force && c.near_frac >= 0.75f && wide_ok) c.mode = kModeRunsWide;
+    // (and in at least three quarters of the sampled blocks individually, see above)
+    if (!force && c.run_frac >= 0.6f && runs_blocks * 4 >= blocks_used * 3) c.mode = kModeRuns;
+    else if (!force && c.near_frac >= 0.75f && near_blocks * 4 >= blocks_used * 3 && wide_ok) c.mode = kModeRunsWide;
     // fixed-point scale: 2^e = the power of two above the largest sampled |w|
     {
         double inv_q = 0.0, q = 0.0, wcap = 0.0;

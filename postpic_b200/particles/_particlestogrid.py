@@ -31,6 +31,31 @@ method = None
 # GPU used for numpy inputs; None = the process's current CUDA device
 device_index = None
 
+# per-thread override of `method` (the module attribute above is process-wide): `with use_method('fixed'): ...`
+import contextlib as _contextlib
+import threading as _threading
+
+_local = _threading.local()
+_UNSET = object()
+
+
+@_contextlib.contextmanager
+def use_method(name):
+    """Deposition method for the calls of THIS thread inside the block (thread-safe, unlike the module attribute)."""
+    if name not in _lib.METHODS:
+        raise ValueError('unknown deposition method {!r}'.format(name))
+    prev = getattr(_local, 'method', _UNSET)
+    _local.method = name
+    try:
+        yield
+    finally:
+        _local.method = prev
+
+
+def _current_method():
+    m = getattr(_local, 'method', _UNSET)
+    return method if m is _UNSET else m
+
 
 def _host_array(a, name):
     if not isinstance(a, np.ndarray):
@@ -78,7 +103,7 @@ def _deposit(coords, names, weights, ranges, bins, shape):
     if on_device:
         torch = _device._torch()
         grid_t = torch.empty(plan.dims, dtype=torch.float64, device=coords[0].device)
-        _device.deposit_into(grid_t, plan, coords, weights, method=method, zero=True)
+        _device.deposit_into(grid_t, plan, coords, weights, method=_current_method(), zero=True)
         grid = grid_t.cpu().numpy()
     else:
         lib = _lib.load()
@@ -95,7 +120,7 @@ def _deposit(coords, names, weights, ranges, bins, shape):
         _lib.check(lib.ptg_histogram_host_f64(
             ndim, plan.shape, n, ptr[0], ptr[1], ptr[2], wptr, cstrides,
             plan.lo.ctypes.data, plan.inv.ctypes.data, plan.cbins, grid.ctypes.data,
-            _lib.METHODS[method], -1 if device_index is None else int(device_index)))
+            _lib.METHODS[_current_method()], -1 if device_index is None else int(device_index)))
     return grid[plan.interior], plan.edges
 
 

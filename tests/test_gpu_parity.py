@@ -667,3 +667,41 @@ def test_bulk_copy_runs_kernel_every_instance_against_the_oracle():
     env = dict(os.environ, PTG_RUNS_IMPL='b')
     r = subprocess.run([sys.executable, '-c', _BULK_SCRIPT, root], env=env, capture_output=True, text=True, timeout=280)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_partially_ordered_dump_and_thread_local_method(ptg, oracle):
+    """A dump that is cell-ordered in its first 70 % and unordered in the rest: AUTO must not be talked into RUNS by the
+    average (the probe asks for ordered blocks, not an ordered mean), and whatever it picks must match the oracle.
+    `use_method` overrides the process-wide knob for one thread only."""
+    import threading
+    import torch
+    from postpic_b200 import device, _lib
+    rng = np.random.default_rng(17)
+    n = 6_000_000
+    x, y, w = rng.random(n), rng.random(n), rng.random(n)
+    k = int(0.7 * n)
+    cell = np.floor(x[:k] * 256) * 256 + np.floor(y[:k] * 256)
+    o = np.argsort(cell, kind='stable')
+    x[:k], y[:k], w[:k] = x[:k][o], y[:k][o], w[:k][o]
+    kw = dict(range=((0, 1), (0, 1)), bins=(256, 256), shape=2)
+    got, _ = device.deposit([torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()], torch.from_numpy(w).cuda(), **kw)
+    assert _lib.last_probe()['mode'] != 'runs'
+    h = oracle.histogram2d(x, y, weights=w, **kw)[0]
+    assert np.max(np.abs(got.cpu().numpy() - h.base)) <= 1e-12 * np.max(np.abs(h.base))
+    # thread-local method
+    seen = {}
+
+    def worker():
+        seen['inner'] = ptg._current_method()
+    with ptg.use_method('fixed'):
+        assert ptg._current_method() == 'fixed'
+        t = threading.Thread(target=worker)
+        t.start()
+        t.join()
+        h1 = ptg.histogram2d(x[:200000], y[:200000], weights=w[:200000], **kw)[0]
+        h2 = ptg.histogram2d(x[:200000], y[:200000], weights=w[:200000], **kw)[0]
+        assert np.array_equal(h1, h2)
+    assert seen['inner'] is None and ptg._current_method() is None
+    with pytest.raises(ValueError):
+        with ptg.use_method('nonsense'):
+            pass
