@@ -1,22 +1,24 @@
-// ptg_deposit_tiled.cu -- method TILED: shared-memory privatised sub-grid tiles.
+// ptg_deposit_tiled.cu -- method TILED: shared-memory privatised sub-grid tiles, and the probe of method AUTO.
 //
 // One persistent CTA per SM walks a contiguous span of the particle arrays and keeps a
 // window ("tile") of the ghost-padded grid in its 200 KB of shared memory:
-//   * particles whose whole stencil falls inside the window are accumulated there
-//     with shared-memory atomics; runs of adjacent lanes that hit the same base cell
-//     (cell-ordered PIC output, tight bunches) are first summed across the warp with
-//     shuffles so that one lane commits the run (warp-aggregated atomics);
+//   * particles whose whole stencil falls inside the window are accumulated there with
+//     shared-memory atomics;
 //   * particles outside the window go straight to the grid in HBM/L2 with RED.F64,
 //     so the result is correct for any input -- the window only decides the speed;
 //   * the CTA watches its hit rate and, when most particles miss, merges the tile
 //     into the global grid and re-centres the window on the particles it is
 //     currently reading; at the end of its span the tile is merged once more.
-// The window *shape* is chosen per launch by a one-CTA probe kernel that looks at 16
-// blocks of 1024 consecutive particles: extents ~ 4 x the mean absolute deviation of
+// The window *shape* is chosen per launch by a 16-CTA probe kernel that looks at 16
+// blocks of 512 consecutive particles: extents ~ 4 x the mean absolute deviation of
 // the stencil base cell inside a block, scaled to the tile budget.  For inputs without
 // locality (i.i.d. positions over a grid much larger than the tile) the probe marks
-// the tile as useless and the launcher's second kernel (method ROWS) does the work.
+// the tile as useless and one of the other kernels launched next to it does the work.
 //
+// Kernels in this file: k_probe; k_deposit_tile_fx (the default windowed tile, fixed point);
+// k_deposit_tiled (the fp64 CAS tile with warp aggregation of runs, PTG_EXACT_ACCUM);
+// k_deposit_small (whole grid in shared memory, up to 32 replicas); k_deposit_oneshot (small
+// calls on small grids in one launch).
 //
 // Accumulation inside the tile (round 2): sm_100a has no native fp64 shared-memory atomic -- atomicAdd(double)
 // is a CAS loop (ATOMS.CAST.SPIN.64) that sustains 48 Gparticles/s for a 2-D TSC stencil -- but it has a
@@ -392,20 +394,17 @@ __device__ __forceinline__ void flush_tile(double *tile, const Window &wd, const
     }
 }
 
-template <int ND, int S, bool W, int TT, bool F, bool FX>
+// (the fp64 tile: method 'tiled_exact' / PTG_EXACT_ACCUM.  The default tile kernel is k_deposit_tile_fx below.)
+template <int ND, int S, bool W, int TT, bool F>
 __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, const TileConfig *cfgp) {
     extern __shared__ double tile[];
     __shared__ long long scratch[34];
     __shared__ Window s_win;
-    __shared__ unsigned s_acc, s_miss, s_full;
+    __shared__ unsigned s_acc, s_miss;
     constexpr int NW = StencilWidth<S>::value;
 
     if (cfgp->mode != kModeTiled) return;
     const TileConfig cfg = *cfgp;
-    // fixed point: scale, weight cap and this lane's share of the tile's 64-bit range (see fx_lane_limit)
-    const double fx_inv_q = cfg.fx_inv_q, fx_q = cfg.fx_q, fx_wcap = cfg.fx_wcap;
-    const double fx_limit = fx_lane_limit(TT, kEvalEvery * kTV) * fx_wcap;
-    double fx_sum = 0.0;
     int cells = 1;
     bool whole = true;                       // the window holds the whole grid (small 1-D / 2-D histograms)
     for (int a = 0; a < ND; ++a) { cells *= cfg.ext[a]; whole = whole && cfg.ext[a] >= P.dims[a]; }
@@ -415,19 +414,13 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
     if (replicas > TT / 32) replicas = TT / 32;
     if (replicas < 1) replicas = 1;
     double *mytile = tile + ((threadIdx.x >> 5) % replicas) * cells;
-    unsigned *mylo = reinterpret_cast<unsigned *>(tile) + ((threadIdx.x >> 5) % replicas) * cells;
 
-    if constexpr (FX) {
-        unsigned *lo = reinterpret_cast<unsigned *>(tile);
-        for (int c = threadIdx.x; c < cells * replicas; c += TT) { lo[c] = 0u; lo[kFxHi + c] = 0u; }
-    } else {
-        for (int c = threadIdx.x; c < cells * replicas; c += TT) tile[c] = 0.0;
-    }
+    for (int c = threadIdx.x; c < cells * replicas; c += TT) tile[c] = 0.0;
     if (threadIdx.x == 0) {
         for (int a = 0; a < 3; ++a) { s_win.e[a] = a < ND ? cfg.ext[a] : 1; s_win.o[a] = 0; }
         // a window that covers the whole axis never needs to move; the others start "nowhere"
         for (int a = 0; a < ND; ++a) if (cfg.ext[a] < P.dims[a]) s_win.o[a] = -(1 << 28);
-        s_acc = 0; s_miss = 0; s_full = 0;
+        s_acc = 0; s_miss = 0;
     }
     __syncthreads();
     Window wd = s_win;
@@ -480,8 +473,6 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
         // ---- stencil in registers --------------------------------------------------
         double wx[NW], wy[NW], wz[NW];
         ok = particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) && i < end && particle_selected(P, i);
-        // fixed point takes weights up to the cap (NaN / inf fail the comparison); the others go to the grid exactly
-        const bool fits = !FX || (fx_inv_q != 0.0 && (!W || fabs(w) <= fx_wcap));
         // value of stencil cell (a, c, d), reference operation order: ((wx*wy)*wz)*w
         auto value = [&](int a, int c, int d) -> double { return stencil_value<ND, S, W>(wx, wy, wz, a, c, d, w); };
         constexpr int NV = ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW;
@@ -499,9 +490,9 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
 #pragma unroll
                     for (int d = 0; d < NDD; ++d) v[(a * NC + c) * NDD + d] = value(a, c, d);
             // ---- warp aggregation of runs of equal base cells -------------------------
-            const int key = ok && fits ? (ND == 1 ? b[0] : ND == 2 ? b[0] * P.dims[1] + b[1]
-                                                                   : (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2])
-                                       : -1 - lane;         // (a particle that does not fit is a run of its own)
+            const int key = ok ? (ND == 1 ? b[0] : ND == 2 ? b[0] * P.dims[1] + b[1]
+                                                           : (b[0] * P.dims[1] + b[1]) * P.dims[2] + b[2])
+                               : -1 - lane;
             const int prev = __shfl_up_sync(0xffffffffu, key, 1);
             const bool head = lane == 0 || prev != key;
             const unsigned heads = __ballot_sync(0xffffffffu, head);
@@ -525,7 +516,7 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
             else return value(a, c, d);
         };
         // ---- deposit: tile if the stencil fits the window, else straight to the grid ----
-        bool hit = commit && fits;
+        bool hit = commit;
 #pragma unroll
         for (int a = 0; a < ND; ++a) hit = hit && b[a] >= wd.o[a] && b[a] + NW <= wd.o[a] + wd.e[a];
         if (hit) {
@@ -536,10 +527,7 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
 #pragma unroll
-                    for (int d = 0; d < NDD; ++d) {
-                        if constexpr (FX) fx_add(mylo, off + (a * p1 + c) * p2 + d, cellval(a, c, d), fx_inv_q);
-                        else atomicAdd(mytile + off + (a * p1 + c) * p2 + d, cellval(a, c, d));
-                    }
+                    for (int d = 0; d < NDD; ++d) atomicAdd(mytile + off + (a * p1 + c) * p2 + d, cellval(a, c, d));
         } else if (commit) {
             const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
             double *g = P.grid + ((int64_t)b[0] * g1 + b[1]) * g2 + b[2];
@@ -558,30 +546,19 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
         const unsigned m_in = __ballot_sync(0xffffffffu, inside);
         acc_w += __popc(m_ok);
         miss_w += __popc(m_ok & ~m_in);
-        // what this lane's particle may have added to a cell of the tile (whoever committed it)
-        if (FX && inside && fits) fx_sum = __dadd_rn(fx_sum, W ? fabs(w) : 1.0);
       }
         if (++since_eval == kEvalEvery && i0 + (int64_t)TT * kTV < end) {
             since_eval = 0;
-            if (threadIdx.x == 0) { s_acc = 0; s_miss = 0; s_full = 0; }
+            if (threadIdx.x == 0) { s_acc = 0; s_miss = 0; }
             __syncthreads();
             if (lane == 0 && acc_w) { atomicAdd(&s_acc, acc_w); atomicAdd(&s_miss, miss_w); }
-            if (FX && fx_sum > 0.0 && fx_sum >= fx_limit) s_full = 1u;
             acc_w = 0; miss_w = 0;
             __syncthreads();
             const unsigned acc = s_acc, miss = s_miss;
             const bool move = acc >= 64 && miss * 2 > acc;
-            const bool full = FX && s_full != 0u;
             __syncthreads();
-            if (full && !move) {
-                // the tile's 64-bit range could be exhausted before the next check: merge it, keep the window
-                flush_tile<ND, TT, FX>(tile, wd, P, cells, replicas, fx_q);
-                fx_sum = 0.0;
-                __syncthreads();
-            }
             if (move) {
-                fx_sum = 0.0;
-                flush_tile<ND, TT, FX>(tile, wd, P, cells, replicas, fx_q);
+                flush_tile<ND, TT, false>(tile, wd, P, cells, replicas, 0.0);
                 // new centre: mean base cell of the sub-chunk in registers
                 const long long cnt = block_sum(ok ? 1 : 0, scratch);
                 long long mean[3] = {0, 0, 0};
@@ -602,7 +579,7 @@ __global__ void __launch_bounds__(TT, 1) k_deposit_tiled(const DepositParams P, 
         }
     }
     __syncthreads();
-    flush_tile<ND, TT, FX>(tile, wd, P, cells, replicas, fx_q);
+    flush_tile<ND, TT, false>(tile, wd, P, cells, replicas, 0.0);
 }
 
 // ---------------------------------------------------------------------------------
@@ -1165,7 +1142,7 @@ static cudaError_t launch_tiled(const DepositParams &P, TileConfig *cfg, int for
     constexpr int NW = StencilWidth<S>::value;
     constexpr int TT = TileThreads<(ND == 1 ? NW : ND == 2 ? NW * NW : NW * NW * NW)>::value;
     const bool fuse = W && fused_mode(P);
-    auto kern = fuse ? k_deposit_tiled<ND, S, W, TT, W, false> : k_deposit_tiled<ND, S, W, TT, false, false>;
+    auto kern = fuse ? k_deposit_tiled<ND, S, W, TT, W> : k_deposit_tiled<ND, S, W, TT, false>;
     const size_t smem = (size_t)kTileCells * sizeof(double);
     // per-device attribute, cheap to set: done on every launch so that any device works
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -286,3 +286,22 @@ def test_shard_bounds_cover_everything():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [b - a for a, b in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_expression_evaluator_accepts_arithmetic_only():
+    """The scalar-expression evaluator (the reference uses numexpr, particles.py:290-330): arithmetic, comparisons and
+    calls of the known functions; everything that could reach Python internals is rejected before evaluation."""
+    import numpy as np
+    import pytest
+    from postpic_b200 import MultiSpecies, ArraySource
+    ms = MultiSpecies(ArraySource.dummy(500, 2, seed=1))
+    x, y = np.asarray(ms('x')), np.asarray(ms('y'))
+    assert np.allclose(ms('x*2 + sqrt(abs(y)) - 3'), x * 2 + np.sqrt(np.abs(y)) - 3)
+    assert np.array_equal(ms('(x > 0) & (y < 0.5)'), (x > 0) & (y < 0.5))
+    assert np.allclose(ms('arctan2(y, x) ** 2'), np.arctan2(y, x) ** 2)
+    for bad in ("().__class__", "x.real", "[v for v in (1,)]", "__import__('os')", "lambda: 1", "x[0]",
+                "sqrt(x, out=y)", "'a' + 'b'", "x if y else x"):
+        with pytest.raises(ValueError):
+            ms(bad)
+    with pytest.raises(KeyError, match='"nope" not found!'):
+        ms('nope + 1')
