@@ -619,6 +619,37 @@ def run_b200_arm(args):
         parity["ok"] = bool(parity["per_bin_max_abs_over_max_bin"] <= 1e-12 and parity["total_abs_over_sum_abs_w"] <= 1e-12)
         del g_s, got, ref, h_ref, hc, hw
 
+    # every named particle shape on this workload at N GPUs (north_star: throughput of each shape at 1/2/4/8 GPUs):
+    # zero grid + deposit + all-reduce per step like `value`, max over ranks, a few steps each
+    shapes_block = None
+    if name == "cfg2" and args.shape is None and fused is None and not args.no_variants:
+        shapes_block = {}
+        for sh in (0, 1, 2, 3):
+            plan_s = ptgdev.Plan(list(ranges), list(bins), sh)
+            grid_s = torch.empty(plan_s.dims, dtype=torch.float64, device=dev)
+
+            def step_s():
+                ptgdev.deposit_into(grid_s, plan_s, coords, w, method=method, zero=True)
+                if world > 1:
+                    dist.all_reduce(grid_s, op=dist.ReduceOp.SUM)
+            for _ in range(3):
+                step_s()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                step_s()
+            b.record()
+            barrier()
+            ms_s = a.elapsed_time(b) / 5
+            if world > 1:
+                t = torch.tensor([ms_s], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_s = float(t.item())
+            shapes_block["shape%d" % sh] = {"value": n * world / ms_s * 1e-6, "unit": UNIT, "ms_per_step": ms_s,
+                                            "roofline_frac_per_gpu": n * bpp / ms_s * 1e-6 / peak}
+            del grid_s
+
     # end to end through the public API with host (pinned) inputs
     e2e = None
     if not args.no_e2e:
@@ -726,7 +757,8 @@ def run_b200_arm(args):
                        "l2": "inputs (%.1f GB per GPU) larger than L2, no flush needed" % (n * bpp * 1e-9),
                        "parallelism": "particles sharded over %d GPU(s), private grids, NCCL all-reduce" % world
                        if world > 1 else "1 GPU", "device": info["name"], "sm_count": info["sm_count"]},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "variants": variants, "configs": configs,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "variants": variants, "shapes": shapes_block,
+            "configs": configs,
             "gpu_launches": args.steps * world * launches_per_step(args.method, nd, shape, n, plan),
             "clocks": clocks.summary(), "parity": parity, "auto_probe": probe,
         }

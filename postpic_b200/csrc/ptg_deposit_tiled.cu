@@ -137,8 +137,12 @@ __device__ __forceinline__ double block_max(double v, long long *scratch /* >= 3
 // commute, so any interleaving of the atomics of different threads gives the same 64-bit sum.
 constexpr int kFxHi = kTileCells;         // hi word of cell c lives kFxHi words after its lo word
 __device__ __forceinline__ void fx_add(unsigned *lo, int c, double v, double inv_q) {
-    const long long q = __double2ll_rn(__dmul_rn(v, inv_q));
-    const unsigned l = (unsigned)q, h = (unsigned)((unsigned long long)q >> 32);
+    // round(v * inv_q) as a 64-bit two's-complement integer without a conversion instruction: inv_q is a power of two, so
+    // the fused multiply-add rounds exactly once (to nearest even, like __double2ll_rn) at unit weight when 1.5 * 2^52 is
+    // added; the low word of the sum's bit pattern IS the low word of the integer, the high word is off by 0x43380000.
+    // (|v * inv_q| <= 4 * 2^45 < 2^51.)
+    const double d = __fma_rn(v, inv_q, 6755399441055744.0);
+    const unsigned l = (unsigned)__double2loint(d), h = (unsigned)__double2hiint(d) - 0x43380000u;
     const unsigned old = atomicAdd(lo + c, l);
     atomicAdd(lo + kFxHi + c, h + ((old + l) < old ? 1u : 0u));
 }
