@@ -66,7 +66,6 @@ __global__ void __launch_bounds__(kFT) k_fixed_deposit(const DepositParams P, co
     const double inv_q = cfg->fx_inv_q;
     const int j = threadIdx.x & 3, group = threadIdx.x >> 2;
     constexpr int kGroups = kFT / 4;
-    const int64_t g1 = ND >= 2 ? P.dims[1] : 1, g2 = ND >= 3 ? P.dims[2] : 1;
     const int64_t span = ((P.n + gridDim.x - 1) / gridDim.x + kGroups - 1) / kGroups * kGroups;
     const int64_t begin = (int64_t)blockIdx.x * span;
     const int64_t end = begin + span < P.n ? begin + span : P.n;
@@ -79,18 +78,34 @@ __global__ void __launch_bounds__(kFT) k_fixed_deposit(const DepositParams P, co
         int b[3];
         double wx[NW], wy[NW], wz[NW];
         if (!particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) || j >= NW) continue;
-        const int64_t lin = ((int64_t)b[0] * g1 + b[1]) * g2 + b[2] + j;
+        // word index of this lane's cell in the accumulators (plain or staggered layout) and the fp64 grid index
+        const int col = ND == 1 ? b[0] : ND == 2 ? b[1] : b[2];
+        const int64_t rowlin = ND == 1 ? 0 : ND == 2 ? b[0] : (int64_t)b[0] * P.dims[1] + b[1];
+        const bool stag = P.fixed_slo != nullptr;
+        unsigned long long *const alo = stag ? P.fixed_slo : P.fixed_lo;
+        long long *const ahi = stag ? P.fixed_shi : P.fixed_hi;
+        const int64_t pitch = stag ? P.fixed_pitch : P.dims[ND - 1];
+        int64_t lin = rowlin * pitch + col + j;
+        if (stag && (NW == 3 ? (col & 2) != 0 : (col & 3) == 3)) lin += P.fixed_copy + 2;
+        const int64_t glin = rowlin * P.dims[ND - 1] + col + j;
+        const int64_t rs = ND == 1 ? 0 : pitch, ss = ND == 3 ? (int64_t)P.dims[1] * pitch : 0;              // accumulators
+        const int64_t grs = ND == 1 ? 0 : P.dims[ND - 1], gss = ND == 3 ? (int64_t)P.dims[1] * P.dims[2] : 0;   // fp64 grid
+        auto put = [&](int64_t off, int64_t goff, double v) {
+            if (fabs(v) <= 1.79769313486231570e308)
+                fixed_accumulate_words(alo + lin + off, ahi + lin + off, P.fixed_split, __double2ll_rn(__dmul_rn(v, inv_q)));
+            else red_add(P.grid + glin + goff, v);
+        };
         const double (&wl)[NW] = ND == 1 ? wx : ND == 2 ? wy : wz;
         double wj = wl[0];
 #pragma unroll
         for (int k = 1; k < NW; ++k) wj = j == k ? wl[k] : wj;
         if (ND == 1) {
-            fixed_add(P, lin, S == 0 ? (W ? w : 1.0) : (W ? __dmul_rn(wj, w) : wj), inv_q);
+            put(0, 0, S == 0 ? (W ? w : 1.0) : (W ? __dmul_rn(wj, w) : wj));
         } else if (ND == 2) {
 #pragma unroll
             for (int a = 0; a < NW; ++a) {
                 const double c = __dmul_rn(wx[a], wj);
-                fixed_add(P, lin + a * g1, S == 0 ? (W ? w : 1.0) : (W ? __dmul_rn(c, w) : c), inv_q);
+                put(a * rs, a * grs, S == 0 ? (W ? w : 1.0) : (W ? __dmul_rn(c, w) : c));
             }
         } else {
 #pragma unroll
@@ -98,7 +113,7 @@ __global__ void __launch_bounds__(kFT) k_fixed_deposit(const DepositParams P, co
 #pragma unroll
                 for (int c2 = 0; c2 < NW; ++c2) {
                     const double c = __dmul_rn(__dmul_rn(wx[a], wy[c2]), wj);
-                    fixed_add(P, lin + (a * g1 + c2) * g2, S == 0 ? (W ? w : 1.0) : (W ? __dmul_rn(c, w) : c), inv_q);
+                    put(a * ss + c2 * rs, a * gss + c2 * grs, S == 0 ? (W ? w : 1.0) : (W ? __dmul_rn(c, w) : c));
                 }
         }
     }
@@ -109,11 +124,20 @@ __global__ void __launch_bounds__(256) k_fixed_finish(const DepositParams P, int
     const double q = cfg->fx_q;
     const int64_t step = (int64_t)gridDim.x * blockDim.x;
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += step) {
-        const unsigned long long lo0 = P.fixed_lo[c];
-        const long long hi0 = P.fixed_hi[c];
-        if (lo0 == 0ull && hi0 == 0ll) continue;
-        // the cell's sum as one 128-bit integer, whichever representation was accumulated
-        __int128 t = P.fixed_split ? ((__int128)hi0 << 31) + (__int128)lo0 : ((__int128)hi0 << 64) + (__int128)lo0;
+        // the cell's sum as one 128-bit integer, whichever representation was accumulated: the plain pair plus, when
+        // the direct kernel used them, both copies of the staggered pair
+        auto word = [&](const unsigned long long *lo, const long long *hi, int64_t i) -> __int128 {
+            const unsigned long long lo0 = lo[i];
+            const long long hi0 = hi[i];
+            return P.fixed_split ? ((__int128)hi0 << 31) + (__int128)lo0 : ((__int128)hi0 << 64) + (__int128)lo0;
+        };
+        __int128 t = word(P.fixed_lo, P.fixed_hi, c);
+        if (P.fixed_slo != nullptr) {
+            const unsigned row = (unsigned)c / (unsigned)P.fixed_last;
+            const int64_t idx = (int64_t)row * P.fixed_pitch + ((unsigned)c - row * (unsigned)P.fixed_last);
+            t += word(P.fixed_slo, P.fixed_shi, idx) + word(P.fixed_slo, P.fixed_shi, P.fixed_copy + idx + 2);
+        }
+        if (t == 0) continue;
         const bool neg = t < 0;
         if (neg) t = -t;                             // magnitude: no cancellation in the conversion below
         const unsigned long long lo = (unsigned long long)t, hi = (unsigned long long)(t >> 64);
@@ -152,16 +176,30 @@ static cudaError_t fixed_s(int shape, const DepositParams &P, const TileConfig *
 cudaError_t deposit_fixed(int ndim, int shape, const DepositParams &P0, TileConfig *cfg, int sm_count, cudaStream_t st) {
     if (P0.n <= 0) return cudaSuccess;
     const int64_t cells = (int64_t)P0.dims[0] * P0.dims[1] * P0.dims[2];
+    // accumulator layout: staggered (two sector-aligned copies, as method ROWS) for stencil rows of 2 or 3 cells
+    const int last = P0.dims[ndim - 1];
+    const int pitch = (last + 2 + 3) / 4 * 4;
+    const int64_t nrows = cells / last;
+    const int64_t copy = (nrows * pitch + 4) / 4 * 4;
+    const bool stagger = (shape == 1 || shape == 2) && ndim >= 2 && P0.n >= (int64_t(1) << 20) &&
+                         (size_t)(2 * copy) * 16 <= ((size_t)96 << 20);
+    const int64_t swords = stagger ? 2 * copy + 4 : 0;
+    const int64_t pwords = (cells + 3) / 4 * 4;          // keeps the staggered copies 32-byte aligned
     void *buf = nullptr;
-    const size_t bytes = (size_t)cells * 16 + sizeof(FixedState);
+    const size_t bytes = (size_t)(pwords + swords) * 16 + sizeof(FixedState);
     cudaError_t e = scratch_alloc(&buf, bytes, st);
     if (e != cudaSuccess) return e;
     auto fail = [&](cudaError_t err) { cudaFreeAsync(buf, st); return err; };
     if ((e = cudaMemsetAsync(buf, 0, bytes, st)) != cudaSuccess) return fail(e);
     DepositParams P = P0;
     P.fixed_lo = static_cast<unsigned long long *>(buf);
-    P.fixed_hi = reinterpret_cast<long long *>(P.fixed_lo + cells);
-    FixedState *state = reinterpret_cast<FixedState *>(P.fixed_lo + 2 * cells);
+    P.fixed_hi = reinterpret_cast<long long *>(P.fixed_lo + pwords);
+    P.fixed_slo = stagger ? P.fixed_lo + 2 * pwords : nullptr;
+    P.fixed_shi = stagger ? reinterpret_cast<long long *>(P.fixed_slo + swords) : nullptr;
+    FixedState *state = reinterpret_cast<FixedState *>(P.fixed_lo + 2 * (pwords + swords));
+    P.fixed_pitch = stagger ? pitch : 0;
+    P.fixed_last = last;
+    P.fixed_copy = stagger ? copy : 0;
     // two fire-and-forget reductions per contribution while no cell can see 2^33 of them, the carry form beyond
     const int nw = shape == 0 ? 1 : shape + 1;
     const int64_t per_particle = ndim == 1 ? nw : ndim == 2 ? nw * nw : nw * nw * nw;

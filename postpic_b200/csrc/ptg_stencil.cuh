@@ -139,6 +139,15 @@ struct DepositParams {
     unsigned long long *fixed_lo;
     long long *fixed_hi;
     int fixed_split;        // representation of the accumulators, see fixed_accumulate()
+    // A second pair of accumulators in the staggered layout of method ROWS, for the kernel that deposits unordered
+    // input directly (k_fixed_deposit); null when not allocated.  Rows of the last axis (fixed_last cells) are padded to
+    // fixed_pitch words, a second copy fixed_copy words further on stores column j at j + 2; a stencil row of 2 or 3
+    // cells goes to the copy in which it does not straddle a 32-byte sector.  Tile merges and miss paths use the plain
+    // pair above (cell c at word c); k_fixed_finish adds everything up.
+    unsigned long long *fixed_slo;
+    long long *fixed_shi;
+    int fixed_pitch, fixed_last;
+    int64_t fixed_copy;
 };
 
 // the kernels' fused (F = true) instances do the work when a weight or an axis expression is evaluated in the kernel
@@ -329,17 +338,21 @@ __device__ __forceinline__ void red_add(double *addr, double v) {
 //   carry (fixed_split = 0): value = hi * 2^64 + lo, a true 128-bit sum: the returning add on the low word tells
 //     whether it wrapped, the high word gets the carry / sign extension.  No limit, ~2x slower (return trips).
 // Integer addition is associative and commutative: the sums do not depend on the order of the atomics.
-__device__ __forceinline__ void fixed_accumulate(const DepositParams &P, int64_t lin, long long k) {
-    if (P.fixed_split) {
-        atomicAdd(P.fixed_lo + lin, (unsigned long long)(k & 0x7fffffffll));
+__device__ __forceinline__ void fixed_accumulate_words(unsigned long long *lo, long long *hi, int split, long long k) {
+    if (split) {
+        atomicAdd(lo, (unsigned long long)(k & 0x7fffffffll));
         const long long h = k >> 31;
-        if (h != 0) atomicAdd(reinterpret_cast<unsigned long long *>(P.fixed_hi + lin), (unsigned long long)h);
+        if (h != 0) atomicAdd(reinterpret_cast<unsigned long long *>(hi), (unsigned long long)h);
     } else {
         const unsigned long long a = (unsigned long long)k;
-        const unsigned long long old = atomicAdd(P.fixed_lo + lin, a);
+        const unsigned long long old = atomicAdd(lo, a);
         const long long h = (k < 0 ? -1ll : 0ll) + ((old + a) < old ? 1ll : 0ll);
-        if (h != 0) atomicAdd(reinterpret_cast<unsigned long long *>(P.fixed_hi + lin), (unsigned long long)h);
+        if (h != 0) atomicAdd(reinterpret_cast<unsigned long long *>(hi), (unsigned long long)h);
     }
+}
+// `lin` = plain linear cell index of the padded grid
+__device__ __forceinline__ void fixed_accumulate(const DepositParams &P, int64_t lin, long long k) {
+    fixed_accumulate_words(P.fixed_lo + lin, P.fixed_hi + lin, P.fixed_split, k);
 }
 // one contribution for method FIXED: finite values as quanta, NaN / inf straight into the fp64 grid (they poison the
 // cell whatever the order)
