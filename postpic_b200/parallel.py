@@ -125,21 +125,23 @@ def bind_to_gpu_numa(device_index):
 
 
 def histogram_host_sharded(coords, weights=None, range=None, bins=None, shape=2, method=None, group=None,
-                           dst=0, device_index=None):
+                           dst=0, device_index=None, local_deposit=None, local_minmax=None):
     """The numpy drop-in over R ranks: every rank passes ITS block of the particles as host numpy arrays.
 
     Each rank streams its block through the library's chunked H2D pipeline into a private padded grid in
     HBM (ptg_deposit_host_f64: the PCIe copy of chunk k+1 overlaps the deposit of chunk k), the grids are
     summed with one NCCL reduce to rank `dst` over NVLink (dst=None: all-reduce), and only that rank copies
     the sum back to the host.  Returns (padded numpy grid or None on the other ranks, plan).  Missing range
-    ends are completed with the global min / max like histogramdd does on one process."""
+    ends are completed with the global min / max like histogramdd does on one process.
+    `local_deposit(grid, plan, coords, weights)` / `local_minmax(array) -> (lo, hi)` replace the CUDA steps (the
+    grid is then a CPU tensor): the gloo tests inject the oracle there to exercise this host logic without a GPU."""
     import ctypes
     import torch
     import torch.distributed as dist
     from . import _lib
     coords = [np.asarray(c) for c in coords]
     nd = len(coords)
-    if device_index is None:
+    if device_index is None and local_deposit is None:
         device_index = torch.cuda.current_device()
     rng = [[None, None] for _ in coords]
     if range is not None:
@@ -155,6 +157,9 @@ def histogram_host_sharded(coords, weights=None, range=None, bins=None, shape=2,
             if c.shape[0] == 0:
                 local.append((float('inf'), float('-inf')))
                 continue
+            if local_minmax is not None:
+                local.append(tuple(local_minmax(c)))
+                continue
             out = (ctypes.c_double * 2)()
             _lib.check(_lib.load().ptg_minmax_host_f64(c.shape[0], c.ctypes.data, c.strides[0] // 8 if c.shape[0] > 1 else 1,
                                                        out, int(device_index)))
@@ -164,8 +169,12 @@ def histogram_host_sharded(coords, weights=None, range=None, bins=None, shape=2,
             rng[a][1] = hi if rng[a][1] is None else rng[a][1]
     b = as_bins(bins[0] if (nd == 1 and np.ndim(bins)) else bins, nd)
     plan = _device.Plan(rng, b, shape)
-    grid = torch.empty(plan.dims, dtype=torch.float64, device=torch.device('cuda', int(device_index)))
-    _device.deposit_host_into(grid, plan, coords, weights, method=method, zero=True)
+    if local_deposit is None:
+        grid = torch.empty(plan.dims, dtype=torch.float64, device=torch.device('cuda', int(device_index)))
+        _device.deposit_host_into(grid, plan, coords, weights, method=method, zero=True)
+    else:
+        grid = torch.zeros(plan.dims, dtype=torch.float64)
+        local_deposit(grid, plan, coords, weights)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         sum_grids(grid, group=group, dst=dst)
         if dst is not None and dist.get_rank(group) != dst:

@@ -55,6 +55,17 @@ def _worker(rank, world, port, outdir):
     # reduce to rank 0 only
     g, plan = parallel.deposit_sharded([tx], None, range=(0, 1), bins=50, shape=1, dst=0, local_deposit=local)
     results["reduce0"] = g.numpy().copy()
+    # the host-array entry (numpy shards in, reduce to rank 0, only rank 0 gets the grid back)
+    def local_np(grid, plan, coords, weights):
+        g, _, _ = ptg_oracle.deposit(list(coords), weights, [(plan.edges[a][0], plan.edges[a][-1]) for a in range(plan.ndim)],
+                                     plan.bins, plan.shape)
+        grid.copy_(torch.from_numpy(g))
+    h, plan = parallel.histogram_host_sharded([x[b:e], y[b:e]], w[b:e], range=((0, 1), None), bins=(32, 24), shape=2, dst=0,
+                                              local_deposit=local_np, local_minmax=lambda a: (a.min(), a.max()))
+    assert (h is None) == (rank != 0)
+    if rank == 0:
+        results["host_sharded"] = h
+        results["host_edges1"] = plan.edges[1]
     np.savez(os.path.join(outdir, "rank%d.npz" % rank), **results)
     dist.barrier()
     dist.destroy_process_group()
@@ -77,3 +88,6 @@ def test_sharded_deposit_world_size_2(tmp_path, oracle):
     assert np.allclose(r0["auto_range"], full, rtol=1e-13, atol=1e-15)
     full, _, _ = oracle.deposit([x], None, [(0, 1)], [50], 1)
     assert np.allclose(r0["reduce0"], full, rtol=1e-13, atol=1e-15)
+    full, edges, _ = oracle.deposit([x, y], w, [(0, 1), (y.min(), y.max())], [32, 24], 2)
+    assert np.allclose(r0["host_sharded"], full, rtol=1e-13, atol=1e-15) and np.array_equal(r0["host_edges1"], edges[1])
+    assert "host_sharded" not in r1
