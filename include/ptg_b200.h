@@ -277,7 +277,11 @@ int ptg_minmax_host_f64(int64_t n, const double *x, int64_t stride, double *out2
  * to a contiguous device array through the same threaded pinned staging ring.  Synchronous.  Used when
  * several passes need the particles (range completion followed by the deposit): one trip over PCIe. */
 int ptg_upload_host_f64(int64_t n, const double *src, int64_t stride, double *dst_device, int device);
-/* release the cached per-device staging buffers and streams of the host entry points */
+/* Release what the library caches per device: the staging ring of the host entry points (3 device slots of
+ * 128 MiB and, once a pageable / strided source has been seen, 3 pinned host slots of 64 MiB, plus a device grid of
+ * the largest padded grid deposited so far), their streams, the side streams / events of method AUTO, the ring of
+ * probe verdicts, and the blocks cached in the library's private stream-ordered memory pool.  All of it is allocated
+ * on first use and kept until this call (or process exit) so that repeated calls pay no allocation.            */
 int ptg_release(void);
 
 /* ---- test hooks (used by tests/ only) ------------------------------------------------- */
