@@ -197,10 +197,11 @@ class ArraySource(object):
                 val = reader.getSpecies(species, name)
             except KeyError:
                 continue
-            if not hasattr(val, '__len__'):                 # (never np.ndim(val): that would materialise a lazy dataset)
-                arrs[name] = float(val)                  # per-species constant (mass, charge, a uniform weight)
+            try:                                            # (never np.ndim(val): that would materialise a lazy dataset)
+                m = len(val)
+            except TypeError:                               # a plain number or a 0-d array: per-species constant
+                arrs[name] = float(val)                     # (mass, charge, a uniform weight)
                 continue
-            m = len(val)
             if n is None:
                 n = m
             elif m != n:
