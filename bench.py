@@ -323,7 +323,8 @@ def kernel_name(verdict, nd, shape, weighted, n, plan, fused=False):
     if verdict == "runs":
         return "k_deposit_runs_bulk" if (nw ** nd <= 16 and not fused) else "k_deposit_runs"
     if verdict == "runs_wide":
-        return "k_deposit_runs_wide"
+        # odd shapes in 2-D: the widened window fed by the copy engine (ptg_deposit_runs_bulkwide.cu)
+        return "k_deposit_runs_bulk_wide" if (nd == 2 and shape in (1, 3) and not fused) else "k_deposit_runs_wide"
     if shape == 0:
         return "k_deposit_global"
     return "k_deposit_quads" if (nd >= 2 and shape in (1, 2) and not fused) else "k_deposit_rows"

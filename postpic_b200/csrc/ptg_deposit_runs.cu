@@ -21,14 +21,12 @@
 #include <cstdlib>
 
 #include "ptg_internal.cuh"
+#include "ptg_runs_common.cuh"
 
 namespace ptg {
 
 // PTG_RUNS_IMPL=b|v forces the bulk-copy / the vector-load kernel wherever it exists (A/B runs, tests)
 
-#ifndef PTG_RUNS_MERGE_MAX_HEADS
-#define PTG_RUNS_MERGE_MAX_HEADS 20      // warp merge only when the 32 lanes hold at most this many runs
-#endif
 #ifndef PTG_RUNS_THREADS
 #define PTG_RUNS_THREADS 256
 #endif
@@ -62,51 +60,6 @@ __device__ __forceinline__ void load_k(const double *base, int64_t stride, int64
 #pragma unroll
         for (int j = 0; j < kRK; ++j) v[j] = __ldg(base + (i + j) * stride);   // L1 keeps the shared sectors
     }
-}
-
-// One run's window -> the grid.  key = padded linear index of the window's first cell.  In a widened window
-// exact zeros are skipped: they carry nothing, and the outermost cells may lie beyond the grid (they can
-// only ever hold zero there).
-template <int MA, int MC, int MD, bool SKIP_ZERO, int MV>
-__device__ __forceinline__ void runs_commit(double *grid, int64_t g1, int64_t g2, int key, const double (&acc)[MV]) {
-    double *g = grid + key;
-#pragma unroll
-    for (int a = 0; a < MA; ++a)
-#pragma unroll
-        for (int c = 0; c < MC; ++c)
-#pragma unroll
-            for (int d = 0; d < MD; ++d) {
-                const double v = acc[(a * MC + c) * MD + d];
-                if (!SKIP_ZERO || v != 0.0) red_add(g + (a * g1 + c) * g2 + d, v);
-            }
-}
-
-// Merge the runs still open at the end of each lane's particles across the warp (segmented shuffle
-// reduction over lanes holding the same window); returns whether this lane has to commit its acc.
-template <int MV>
-__device__ __forceinline__ bool runs_warp_merge(int cur, double (&acc)[MV], int lane) {
-    const int key = cur >= 0 ? cur : -1 - lane;
-    const int prev = __shfl_up_sync(0xffffffffu, key, 1);
-    const bool head = lane == 0 || prev != key;
-    const unsigned heads = __ballot_sync(0xffffffffu, head);
-    bool mine = cur >= 0;
-    if (__popc(heads) <= PTG_RUNS_MERGE_MAX_HEADS) {
-        const unsigned above = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
-        const int next_head = above ? __ffs(above) - 1 : 32;
-#pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) {
-            const bool take = lane + dd < next_head;
-#pragma unroll
-            for (int k = 0; k < MV; ++k) {
-                const double o = __shfl_down_sync(0xffffffffu, acc[k], dd);
-                // predicated add (one @P DADD) instead of the add + two 32-bit selects nvcc emits
-                asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}"
-                    : "+d"(acc[k]) : "d"(o), "r"((int)take));
-            }
-        }
-        mine = mine && head;
-    }
-    return mine;
 }
 
 // resident CTAs per SM asked of ptxas: 4 (64 registers) for register windows of up to 9 cells
@@ -275,59 +228,6 @@ __global__ void __launch_bounds__(kRT, RunsMinBlocks<ND, S, WD>::value) k_deposi
 // those of k_deposit_runs.  No load instruction waits on HBM any more: the only thing a warp can stall
 // on is a tile that has not landed.
 // ---------------------------------------------------------------------------------
-#ifndef PTG_BULK_PER
-#define PTG_BULK_PER 8
-#endif
-#ifndef PTG_BULK_WARPS
-#define PTG_BULK_WARPS 16
-#endif
-#ifndef PTG_BULK_STAGES
-#define PTG_BULK_STAGES 2
-#endif
-#ifndef PTG_BULK_INTERLEAVE
-#define PTG_BULK_INTERLEAVE 0
-#endif
-constexpr int kBulkPer = PTG_BULK_PER;           // consecutive particles per lane and tile
-constexpr int kBulkTile = 32 * kBulkPer;         // particles per warp tile
-template <int ND, bool W> struct BulkCfg {
-    static constexpr int NA = ND + (W ? 1 : 0);                         // arrays streamed
-    static constexpr int STAGES = NA <= 2 ? PTG_BULK_STAGES + 1 : PTG_BULK_STAGES;
-    static constexpr int TILE_BYTES = NA * kBulkTile * 8;               // one stage of one warp
-    static constexpr int FIT = (200 * 1024) / (STAGES * TILE_BYTES) / 4 * 4;
-    static constexpr int WARPS = FIT >= PTG_BULK_WARPS ? PTG_BULK_WARPS : FIT;
-    static constexpr int THREADS = WARPS * 32;
-    static constexpr size_t SMEM = (size_t)WARPS * STAGES * (TILE_BYTES + 16) + WARPS * 128;   // + full / empty barriers, + one word per lane
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); the particle
-// stream is touched once: evict-first in L2
-__device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
-    const uint32_t a = smem_u32(bar);
-    unsigned done = 0;
-    for (unsigned spins = 0; !done; ++spins) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
-        if (spins > (1u << 28)) __trap();            // a tile that never lands is a bug, not a reason to hang the GPU
-    }
-}
-
 template <int ND, int S, bool W>
 __global__ void __launch_bounds__(BulkCfg<ND, W>::THREADS, 1) k_deposit_runs_bulk(const DepositParams P, const TileConfig *gate) {
     if (gate != nullptr && gate->mode != kModeRuns) return;
@@ -534,6 +434,8 @@ static cudaError_t launch_runs(const DepositParams &P, const TileConfig *gate, b
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
     if (wide) {
+        // odd shapes in 2-D, CIC in 3-D: the widened window fed by the copy engine (ptg_deposit_runs_bulkwide.cu)
+        if (runs_bulk_wide_applies(ND, S, P)) return deposit_runs_bulk_wide(ND, S, P, gate, sm_count, st);
         if constexpr (WideOk<ND, S>::value) {
             if (W && fused_mode(P)) {
                 if (vec) k_deposit_runs<ND, S, W, true, 1, W><<<blocks, kRT, 0, st>>>(P, gate);

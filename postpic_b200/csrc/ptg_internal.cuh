@@ -63,6 +63,10 @@ cudaError_t deposit_oneshot(int ndim, int shape, const DepositParams &P, TileCon
 cudaError_t deposit_runs(int ndim, int shape, const DepositParams &P, const TileConfig *gate, bool wide, int sm_count,
                          cudaStream_t st);
 bool runs_wide_available(int ndim, int shape);
+// ptg_deposit_runs_bulkwide.cu -- the widened-window kernel with the particle stream on the copy engine
+bool runs_bulk_wide_applies(int ndim, int shape, const DepositParams &P);
+cudaError_t deposit_runs_bulk_wide(int ndim, int shape, const DepositParams &P, const TileConfig *gate, int sm_count,
+                                   cudaStream_t st);
 
 // ptg_deposit_sorted.cu -- deterministic sort-by-cell + segmented reduce; needs a workspace of
 // sorted_workspace_bytes(n, cells) bytes
