@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kFT) k_fixed_deposit(const DepositParams P, co
         const double w = W ? particle_weight<F>(P, i) : 1.0;
         int b[3];
         double wx[NW], wy[NW], wz[NW];
-        if (!particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) || j >= NW) continue;
+        if (!particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) || j >= NW || b[0] < P.slab_lo || b[0] >= P.slab_hi) continue;
         // word index of this lane's cell in the accumulators (plain or staggered layout) and the fp64 grid index
         const int col = ND == 1 ? b[0] : ND == 2 ? b[1] : b[2];
         const int64_t rowlin = ND == 1 ? 0 : ND == 2 ? b[0] : (int64_t)b[0] * P.dims[1] + b[1];
@@ -221,12 +221,29 @@ cudaError_t deposit_fixed(int ndim, int shape, const DepositParams &P0, TileConf
     // probe (+ the exact quantum) + the shared-memory tile kernel when the input mostly hits a window ...
     if ((e = deposit_tiled(ndim, shape, P, cfg, false, false, sm_count, st, state)) != cudaSuccess) return fail(e);
     // ... and the direct kernel for everything else
-    switch (ndim) {
-        case 1: e = fixed_s<1>(shape, P, cfg, sm_count, st); break;
-        case 2: e = fixed_s<2>(shape, P, cfg, sm_count, st); break;
-        default: e = fixed_s<3>(shape, P, cfg, sm_count, st); break;
+    // Accumulators larger than L2 (cfg3: 258^3 x 16 B = 275 MB) make nearly every reduction miss; as in method ROWS
+    // (ptg_deposit_global.cu) such grids are deposited in slab passes over axis 0, each pass re-reading the particles
+    // but reducing into an L2-resident slice.  Integer sums: the passes change nothing in the result.  cfg3 i.i.d.:
+    // 3.6 -> 7.3 Gp/s with 72 MiB slices (100 / 48 / 36 MiB: 7.1 / 5.6 / 4.6; profiles/r02/perf_fixed_slabs.log).  Deciding
+    // on axis 0 before the other loads was measured and is slower (5.9 Gp/s: the warp diverges and loses its
+    // load-level parallelism, perf_fixed_slabs_earlyout.log).
+    int passes = 1;
+    {
+        static const int64_t slab_mb = [] { const char *s = getenv("PTG_FIXED_SLAB_MB"); int64_t v = s ? atoll(s) : 72; return v < 1 ? 1 : v; }();
+        const int64_t acc_bytes = cells * 16;
+        if (acc_bytes > ((int64_t)96 << 20) && P.n >= (int64_t(1) << 22)) passes = (int)((acc_bytes + (slab_mb << 20) - 1) / (slab_mb << 20));
+        if (passes > P.dims[0]) passes = P.dims[0];
     }
-    if (e != cudaSuccess) return fail(e);
+    for (int s = 0; s < passes; ++s) {
+        P.slab_lo = s == 0 ? -(1 << 30) : (int)((int64_t)P.dims[0] * s / passes);
+        P.slab_hi = s == passes - 1 ? (1 << 30) : (int)((int64_t)P.dims[0] * (s + 1) / passes);
+        switch (ndim) {
+            case 1: e = fixed_s<1>(shape, P, cfg, sm_count, st); break;
+            case 2: e = fixed_s<2>(shape, P, cfg, sm_count, st); break;
+            default: e = fixed_s<3>(shape, P, cfg, sm_count, st); break;
+        }
+        if (e != cudaSuccess) return fail(e);
+    }
     int64_t fb = (cells + 255) / 256;
     int64_t cap = (int64_t)sm_count * 8;
     k_fixed_finish<<<(int)(fb < cap ? fb : cap), 256, 0, st>>>(P, cells, cfg);

@@ -157,3 +157,50 @@ print("HASH", *out)
         assert p.returncode == 0, p.stderr[-2000:]
         res[tag] = [l for l in p.stdout.splitlines() if l.startswith("HASH")][0]
     assert res["split"] == res["carry"]
+
+
+def test_fixed_slab_passes_on_a_grid_larger_than_l2():
+    """Accumulators beyond 96 MB (here 192 x 192 x 176 cells x 16 B = 104 MB) are deposited in slab passes over axis 0
+    (ptg_deposit_fixed.cu).  Integer sums: the grid must carry the same bits whatever the slab size (PTG_FIXED_SLAB_MB
+    is read once per process, hence the child processes) and whatever the particle order, and agree with the oracle."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from postpic_b200 import device
+rng = np.random.default_rng(4242)
+n = 5_000_000
+c = [rng.uniform(-0.03, 1.03, n) for _ in range(3)]
+w = rng.uniform(-0.4, 1.0, n)
+kw = dict(range=[(0, 1)] * 3, bins=(190, 190, 174), shape=1, method='fixed')
+dc = [torch.from_numpy(a).cuda() for a in c]
+dw = torch.from_numpy(w).cuda()
+g1, _ = device.deposit(dc, dw, **kw)
+perm = torch.randperm(n, device='cuda')
+g2, _ = device.deposit([a[perm] for a in dc], dw[perm], **kw)
+assert torch.equal(g1, g2)
+np.save(sys.argv[1], g1.cpu().numpy())
+''' % root
+    grids = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for mb in ("16", "72", "4096"):                       # 7 passes, 2 passes, a single pass
+            e = dict(os.environ)
+            e["PTG_FIXED_SLAB_MB"] = mb
+            out = os.path.join(tmp, "g%s.npy" % mb)
+            p = subprocess.run([sys.executable, "-c", code, out], env=e, capture_output=True, text=True, timeout=300)
+            assert p.returncode == 0, p.stderr[-2000:]
+            grids[mb] = np.load(out)
+    assert np.array_equal(grids["16"], grids["72"]) and np.array_equal(grids["16"], grids["4096"])
+    from oracle import ptg_oracle
+    rng = np.random.default_rng(4242)
+    n = 5_000_000
+    c = [rng.uniform(-0.03, 1.03, n) for _ in range(3)]
+    w = rng.uniform(-0.4, 1.0, n)
+    ho, _ = cases.call(ptg_oracle, c, w, 1, ranges=[(0, 1)] * 3, bins=(190, 190, 174))
+    b = cases.padded(ho)
+    a = grids["72"].reshape(b.shape)
+    assert np.max(np.abs(a - b)) <= 1e-12 * np.max(np.abs(b))
