@@ -18,7 +18,8 @@ LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libptg_b200.so")
 INCLUDE = os.path.join(os.path.dirname(PKG), "include")
 
-SOURCES = ["ptg_capi.cu", "ptg_deposit_global.cu", "ptg_deposit_tiled.cu", "ptg_deposit_sorted.cu", "ptg_deposit_runs.cu", "ptg_deposit_runs_bulkwide.cu", "ptg_deposit_fixed.cu", "ptg_util.cu"]
+SOURCES = ["ptg_capi.cu", "ptg_deposit_global.cu", "ptg_deposit_tiled.cu", "ptg_deposit_tiled_nd1.cu", "ptg_deposit_tiled_nd2.cu", "ptg_deposit_tiled_nd3.cu",
+           "ptg_deposit_sorted.cu", "ptg_deposit_runs.cu", "ptg_deposit_runs_nd1.cu", "ptg_deposit_runs_nd2.cu", "ptg_deposit_runs_nd3.cu", "ptg_deposit_runs_bulkwide.cu", "ptg_deposit_fixed.cu", "ptg_util.cu"]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

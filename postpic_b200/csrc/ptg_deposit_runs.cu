@@ -473,6 +473,21 @@ static cudaError_t runs_s(int shape, const DepositParams &P, const TileConfig *g
     }
 }
 
+// One translation unit per number of axes: this file is compiled four times (postpic_b200/build.py) -- as itself it
+// holds the dispatcher only, ptg_deposit_runs_nd{1,2,3}.cu include it with PTG_ND set and instantiate the kernels of
+// that dimensionality (the build is bound by its longest translation unit).
+#define PTG_CAT2(a, b) a##b
+#define PTG_CAT(a, b) PTG_CAT2(a, b)
+#ifdef PTG_ND
+cudaError_t PTG_CAT(deposit_runs_nd, PTG_ND)(int shape, const DepositParams &P, const TileConfig *gate, bool wide, int sm_count,
+                                             cudaStream_t st) {
+    return runs_s<PTG_ND>(shape, P, gate, wide, sm_count, st);
+}
+#else
+cudaError_t deposit_runs_nd1(int, const DepositParams &, const TileConfig *, bool, int, cudaStream_t);
+cudaError_t deposit_runs_nd2(int, const DepositParams &, const TileConfig *, bool, int, cudaStream_t);
+cudaError_t deposit_runs_nd3(int, const DepositParams &, const TileConfig *, bool, int, cudaStream_t);
+
 bool runs_wide_available(int ndim, int shape) {
     const int mw = (shape == 0 ? 1 : shape + 1) + 1;
     int mv = 1;
@@ -483,10 +498,11 @@ bool runs_wide_available(int ndim, int shape) {
 cudaError_t deposit_runs(int ndim, int shape, const DepositParams &P, const TileConfig *gate, bool wide, int sm_count,
                          cudaStream_t st) {
     switch (ndim) {
-        case 1: return runs_s<1>(shape, P, gate, wide, sm_count, st);
-        case 2: return runs_s<2>(shape, P, gate, wide, sm_count, st);
-        default: return runs_s<3>(shape, P, gate, wide, sm_count, st);
+        case 1: return deposit_runs_nd1(shape, P, gate, wide, sm_count, st);
+        case 2: return deposit_runs_nd2(shape, P, gate, wide, sm_count, st);
+        default: return deposit_runs_nd3(shape, P, gate, wide, sm_count, st);
     }
 }
+#endif
 
 }  // namespace ptg

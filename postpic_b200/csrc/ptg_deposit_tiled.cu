@@ -1123,6 +1123,21 @@ static cudaError_t oneshot_s(int shape, const DepositParams &P, TileConfig *cfg,
 
 // (calls of a few thousand particles keep the path without a sample, which adds every contribution in fp64: a single
 // particle is then deposited bit for bit like the reference does)
+#define PTG_CAT2(a, b) a##b
+#define PTG_CAT(a, b) PTG_CAT2(a, b)
+// One translation unit per number of axes: this file is compiled four times (postpic_b200/build.py) -- as itself it
+// holds the dispatchers only, ptg_deposit_tiled_nd{1,2,3}.cu include it with PTG_ND set and instantiate the kernels
+// of that dimensionality (the build is bound by its longest translation unit).
+#ifdef PTG_ND
+cudaError_t PTG_CAT(deposit_oneshot_nd, PTG_ND)(int shape, const DepositParams &P, TileConfig *cfg, bool zero_first, int sm_count,
+                                                cudaStream_t st) {
+    return oneshot_s<PTG_ND>(shape, P, cfg, zero_first, sm_count, st);
+}
+#else
+cudaError_t deposit_oneshot_nd1(int, const DepositParams &, TileConfig *, bool, int, cudaStream_t);
+cudaError_t deposit_oneshot_nd2(int, const DepositParams &, TileConfig *, bool, int, cudaStream_t);
+cudaError_t deposit_oneshot_nd3(int, const DepositParams &, TileConfig *, bool, int, cudaStream_t);
+
 bool oneshot_applies(const DepositParams &P, int sm_count) {
     return P.n >= 4096 && P.n < (int64_t(1) << 21) && P.n <= (int64_t)sm_count * 16384 &&
            (int64_t)P.dims[0] * P.dims[1] * P.dims[2] <= kOneShotCells;
@@ -1131,11 +1146,12 @@ bool oneshot_applies(const DepositParams &P, int sm_count) {
 cudaError_t deposit_oneshot(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool zero_first, int sm_count,
                             cudaStream_t st) {
     switch (ndim) {
-        case 1: return oneshot_s<1>(shape, P, cfg, zero_first, sm_count, st);
-        case 2: return oneshot_s<2>(shape, P, cfg, zero_first, sm_count, st);
-        default: return oneshot_s<3>(shape, P, cfg, zero_first, sm_count, st);
+        case 1: return deposit_oneshot_nd1(shape, P, cfg, zero_first, sm_count, st);
+        case 2: return deposit_oneshot_nd2(shape, P, cfg, zero_first, sm_count, st);
+        default: return deposit_oneshot_nd3(shape, P, cfg, zero_first, sm_count, st);
     }
 }
+#endif
 
 // ---------------------------------------------------------------------------------
 // launchers
@@ -1197,14 +1213,25 @@ static cudaError_t tiled_s(int shape, const DepositParams &P, TileConfig *cfg, i
     }
 }
 
+#ifdef PTG_ND
+cudaError_t PTG_CAT(deposit_tiled_nd, PTG_ND)(int shape, const DepositParams &P, TileConfig *cfg, bool force, bool exact,
+                                              int sm_count, cudaStream_t st, const FixedState *fixed, cudaEvent_t after_probe) {
+    return tiled_s<PTG_ND>(shape, P, cfg, force, exact, sm_count, st, fixed, after_probe);
+}
+#else
+cudaError_t deposit_tiled_nd1(int, const DepositParams &, TileConfig *, bool, bool, int, cudaStream_t, const FixedState *, cudaEvent_t);
+cudaError_t deposit_tiled_nd2(int, const DepositParams &, TileConfig *, bool, bool, int, cudaStream_t, const FixedState *, cudaEvent_t);
+cudaError_t deposit_tiled_nd3(int, const DepositParams &, TileConfig *, bool, bool, int, cudaStream_t, const FixedState *, cudaEvent_t);
+
 cudaError_t deposit_tiled(int ndim, int shape, const DepositParams &P, TileConfig *cfg, bool force, bool exact,
                           int sm_count, cudaStream_t st, const FixedState *fixed, cudaEvent_t after_probe) {
     if (P.n <= 0) return cudaSuccess;
     switch (ndim) {
-        case 1: return tiled_s<1>(shape, P, cfg, force, exact, sm_count, st, fixed, after_probe);
-        case 2: return tiled_s<2>(shape, P, cfg, force, exact, sm_count, st, fixed, after_probe);
-        default: return tiled_s<3>(shape, P, cfg, force, exact, sm_count, st, fixed, after_probe);
+        case 1: return deposit_tiled_nd1(shape, P, cfg, force, exact, sm_count, st, fixed, after_probe);
+        case 2: return deposit_tiled_nd2(shape, P, cfg, force, exact, sm_count, st, fixed, after_probe);
+        default: return deposit_tiled_nd3(shape, P, cfg, force, exact, sm_count, st, fixed, after_probe);
     }
 }
+#endif
 
 }  // namespace ptg
