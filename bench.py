@@ -741,7 +741,8 @@ def run_b200_arm(args):
                  ("cfg5 AUTO (1e9)", "cfg5", int(1e9), "random", "auto", None, False, 3, None),
                  ("cfg5 deterministic SORTED (2e8)", "cfg5", int(2e8), "random", "sorted", None, False, 2, "reproducible"),
                  ("cfg5 deterministic FIXED: integer accumulation (1e9)", "cfg5", int(1e9), "random", "fixed", None, False, 3, "reproducible"),
-                 ("cfg2 deterministic FIXED: integer accumulation (1e8)", "cfg2", int(1e8), "random", "fixed", None, False, 5, "reproducible")]
+                 ("cfg2 deterministic FIXED: integer accumulation (1e8)", "cfg2", int(1e8), "random", "fixed", None, False, 5, "reproducible"),
+                 ("cfg3 deterministic FIXED: slab passes over a 275 MB accumulator (1.25e8)", "cfg3", int(1.25e8), "random", "fixed", None, False, 2, "reproducible")]
         for tag, nm, nn, order, meth, shp, fz, st, extra in plan_:
             try:
                 configs.append(measure_config(tag, nm, nn, order, meth, dev, peak, shape=shp, fused=fz, steps=st, extra=extra))
