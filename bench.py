@@ -691,6 +691,13 @@ def run_b200_arm(args):
             allv = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
             dist.all_gather(allv, torch.tensor(h2d_gbs, dtype=torch.float64, device=dev))
             h2d_gbs = [float(v.item()) for v in allv]
+        # where this rank's GPU hangs and where its pinned input landed (NUMA node -> pages), gathered on rank 0
+        numa_diag = {"gpu_node": parallel.gpu_numa_node(local_rank), "cpus_bound": len(numa_cpus) if numa_cpus else None,
+                     "pinned_pages_by_node": parallel.numa_pages_of(np_c[0].ctypes.data)}
+        if world > 1:
+            alld = [None] * world
+            dist.all_gather_object(alld, numa_diag)
+            numa_diag = alld
         pageable = None
         if world == 1:
             # the same call on ordinary (pageable) numpy arrays, as a postpic user would pass them
@@ -704,7 +711,7 @@ def run_b200_arm(args):
             del pg_c, pg_w
         e2e = {"value": n * world / dt * 1e-9, "unit": UNIT, "h2d_bytes_per_step": n * bpp, "pageable_value": pageable,
                "d2h_bytes_per_step": plan.cells * 8, "ms_per_step": dt * 1e3, "steps": ksteps,
-               "h2d_deposit_stage_gbs_per_rank": h2d_gbs, "numa_cpus_bound": len(numa_cpus) if numa_cpus else None,
+               "h2d_deposit_stage_gbs_per_rank": h2d_gbs, "numa_cpus_bound": len(numa_cpus) if numa_cpus else None, "numa": numa_diag,
                "api": "postpic_b200.histogramdd(numpy views of pinned host memory)" if world == 1 else
                       "postpic_b200.parallel.histogram_host_sharded(numpy views of pinned host memory): chunked H2D "
                       "pipeline per rank + NCCL reduce to rank 0 + grid D2H on rank 0"}

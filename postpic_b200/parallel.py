@@ -102,12 +102,64 @@ def deposit_sharded(coords, weights=None, range=None, bins=None, shape=2, method
 
 
 
+def gpu_numa_node(device_index):
+    """NUMA node of GPU `device_index`'s PCIe root as sysfs reports it (None when unknown)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        with open("/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:].lower(), rest.lower())) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def prefer_numa_node(node):
+    """set_mempolicy(MPOL_PREFERRED, {node}) for this thread (inherited by the threads it starts): pages this process
+    allocates from now on -- the pinned buffers above all -- come from `node` whichever CPU the thread runs on (the CPU
+    binding alone decides nothing when the container's cpuset holds no CPU of that node).  Returns True on success."""
+    import ctypes
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238           # x86_64
+        return libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(16 * 64 + 1)) == 0
+    except Exception:
+        return False
+
+
+def numa_pages_of(address):
+    """{node: pages} of the mapping that holds `address`, from /proc/self/numa_maps (diagnostics: where did a pinned
+    buffer land); None when the file cannot be read."""
+    try:
+        best = None
+        with open("/proc/self/numa_maps") as f:
+            for line in f:
+                parts = line.split()
+                start = int(parts[0], 16)
+                if start <= address and (best is None or start > best[0]):
+                    best = (start, parts)
+        if best is None:
+            return None
+        return {int(p[1:].split("=")[0]): int(p.split("=")[1]) for p in best[1] if p[0] == "N" and "=" in p and p[1].isdigit()}
+    except Exception:
+        return None
+
+
 def bind_to_gpu_numa(device_index):
-    """Pin this process to the CPUs NVML reports as local to GPU `device_index`, so that the pinned host
-    buffers it allocates afterwards (first touch) and the staging threads of the host pipeline sit on the
-    NUMA node the GPU's PCIe root hangs off.  Returns the CPU list, or None when NVML / the affinity call is
-    not available (nothing is changed then)."""
+    """Pin this process to the CPUs NVML reports as local to GPU `device_index` and prefer the memory of the GPU's NUMA
+    node, so that the pinned host buffers it allocates afterwards and the staging threads of the host pipeline sit on
+    the NUMA node the GPU's PCIe root hangs off.  Returns the CPU list, or None when NVML / the affinity call is not
+    available or the process may not run on any of those CPUs (the memory preference is still tried then)."""
     import os
+    node = gpu_numa_node(device_index)
+    if node is not None and os.environ.get("PTG_NO_MEMPOLICY") is None:
+        prefer_numa_node(node)
     try:
         import pynvml
         pynvml.nvmlInit()
