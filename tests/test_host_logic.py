@@ -305,3 +305,17 @@ def test_expression_evaluator_accepts_arithmetic_only():
             ms(bad)
     with pytest.raises(KeyError, match='"nope" not found!'):
         ms('nope + 1')
+
+
+def test_numa_helpers_do_not_raise():
+    """parallel.bind_to_gpu_numa's helpers are best effort: on a box without NVML / NUMA information they return
+    None / False instead of raising, and numa_pages_of reads this process's own map."""
+    import numpy as np
+    from postpic_b200 import parallel
+    assert parallel.gpu_numa_node(0) is None or parallel.gpu_numa_node(0) >= 0
+    a = np.ones(1 << 20)
+    pages = parallel.numa_pages_of(a.ctypes.data)
+    assert pages is None or (isinstance(pages, dict) and all(v >= 0 for v in pages.values()))
+    assert parallel.prefer_numa_node(0) in (True, False)
+    cpus = parallel.bind_to_gpu_numa(0)
+    assert cpus is None or len(cpus) > 0
