@@ -225,8 +225,9 @@ cudaError_t deposit_fixed(int ndim, int shape, const DepositParams &P0, TileConf
     // (ptg_deposit_global.cu) such grids are deposited in slab passes over axis 0, each pass re-reading the particles
     // but reducing into an L2-resident slice.  Integer sums: the passes change nothing in the result.  cfg3 i.i.d.:
     // 3.6 -> 7.3 Gp/s with 72 MiB slices (100 / 48 / 36 MiB: 7.1 / 5.6 / 4.6; profiles/r02/perf_fixed_slabs.log).  Deciding
-    // on axis 0 before the other loads was measured and is slower (5.9 Gp/s: the warp diverges and loses its
-    // load-level parallelism, perf_fixed_slabs_earlyout.log).
+    // on axis 0 before the other loads was measured and is slower (5.9 Gp/s: the warp diverges,
+    // perf_fixed_slabs_earlyout.log), and so is batching the loads (6.2 Gp/s, perf_fixed_batched_rejected.log); one pass is
+    // issue-bound (ncu_full_fixed_direct_slab_cfg3.txt).
     int passes = 1;
     {
         static const int64_t slab_mb = [] { const char *s = getenv("PTG_FIXED_SLAB_MB"); int64_t v = s ? atoll(s) : 72; return v < 1 ? 1 : v; }();
