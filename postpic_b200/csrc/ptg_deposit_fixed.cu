@@ -69,15 +69,15 @@ __global__ void __launch_bounds__(kFT) k_fixed_deposit(const DepositParams P, co
     const int64_t span = ((P.n + gridDim.x - 1) / gridDim.x + kGroups - 1) / kGroups * kGroups;
     const int64_t begin = (int64_t)blockIdx.x * span;
     const int64_t end = begin + span < P.n ? begin + span : P.n;
-    for (int64_t i = begin + group; i < end; i += kGroups) {
-        if (!particle_selected(P, i)) continue;
+    auto deposit_one = [&](int64_t i) {
+        if (!particle_selected(P, i)) return;
         const double x = particle_coord<F>(P, 0, i);
         const double y = ND >= 2 ? particle_coord<F>(P, 1, i) : 0.0;
         const double z = ND >= 3 ? particle_coord<F>(P, 2, i) : 0.0;
         const double w = W ? particle_weight<F>(P, i) : 1.0;
         int b[3];
         double wx[NW], wy[NW], wz[NW];
-        if (!particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) || j >= NW || b[0] < P.slab_lo || b[0] >= P.slab_hi) continue;
+        if (!particle_stencil<ND, S>(P, x, y, z, b, wx, wy, wz) || j >= NW || b[0] < P.slab_lo || b[0] >= P.slab_hi) return;
         // word index of this lane's cell in the accumulators (plain or staggered layout) and the fp64 grid index
         const int col = ND == 1 ? b[0] : ND == 2 ? b[1] : b[2];
         const int64_t rowlin = ND == 1 ? 0 : ND == 2 ? b[0] : (int64_t)b[0] * P.dims[1] + b[1];
@@ -116,7 +116,40 @@ __global__ void __launch_bounds__(kFT) k_fixed_deposit(const DepositParams P, co
                     put(a * ss + c2 * rs, a * gss + c2 * grs, S == 0 ? (W ? w : 1.0) : (W ? __dmul_rn(c, w) : c));
                 }
         }
+    };
+    if (P.slab_lo > -(1 << 30) || P.slab_hi < (1 << 30)) {
+        // Slab pass: most particles belong to another pass.  Every LANE looks at one particle's axis-0 cell (the same
+        // accept test and base cell as particle_stencil), the warp votes, and only the survivors -- compacted eight at
+        // a time onto the eight 4-lane groups -- get the full stencil: one cheap test per particle instead of a whole
+        // stencil evaluation on four lanes for particles that are then discarded (the kernel is issue-bound,
+        // profiles/r02/ncu_full_fixed_direct_slab_cfg3.txt).  Integer sums: the order change alters nothing.
+        const int lane = threadIdx.x & 31;
+        for (int64_t base = begin + (threadIdx.x >> 5) * 32; base < end; base += kFT) {
+            const int64_t i = base + lane;
+            bool keep = false;
+            if (i < end && particle_selected(P, i)) {
+                const double x = particle_coord<F>(P, 0, i);
+                int b0 = 0;
+                bool in;
+                if constexpr (S == 0) {
+                    in = ngp_axis(x, P.lo[0], P.inv[0], P.fbins[0], b0);
+                } else {
+                    double t[NW];
+                    in = shape_axis<S, false>(x, P.lo[0], P.inv[0], P.fbins_p1[0], b0, t);
+                }
+                keep = in && b0 >= P.slab_lo && b0 < P.slab_hi;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, keep);
+            while (m != 0u) {                                        // (uniform across the warp)
+                const unsigned src = __fns(m, 0u, (lane >> 2) + 1);  // group g takes the g-th survivor
+                if (src != 0xffffffffu) deposit_one(base + src);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) m &= m - 1u;             // drop the eight just served (0 & anything stays 0)
+            }
+        }
+        return;
     }
+    for (int64_t i = begin + group; i < end; i += kGroups) deposit_one(i);
 }
 
 // grid[c] += (128-bit sum of cell c) * q: one thread per cell, one conversion, no atomics
@@ -225,9 +258,9 @@ cudaError_t deposit_fixed(int ndim, int shape, const DepositParams &P0, TileConf
     // (ptg_deposit_global.cu) such grids are deposited in slab passes over axis 0, each pass re-reading the particles
     // but reducing into an L2-resident slice.  Integer sums: the passes change nothing in the result.  cfg3 i.i.d.:
     // 3.6 -> 7.3 Gp/s with 72 MiB slices (100 / 48 / 36 MiB: 7.1 / 5.6 / 4.6; profiles/r02/perf_fixed_slabs.log).  Deciding
-    // on axis 0 before the other loads was measured and is slower (5.9 Gp/s: the warp diverges,
+    // on axis 0 per 4-lane group was measured and is slower (5.9 Gp/s: the warp diverges without shedding work,
     // perf_fixed_slabs_earlyout.log), and so is batching the loads (6.2 Gp/s, perf_fixed_batched_rejected.log); one pass is
-    // issue-bound (ncu_full_fixed_direct_slab_cfg3.txt).
+    // issue-bound (ncu_full_fixed_direct_slab_cfg3.txt) -- hence the vote-and-compact form of the kernel's slab branch.
     int passes = 1;
     {
         static const int64_t slab_mb = [] { const char *s = getenv("PTG_FIXED_SLAB_MB"); int64_t v = s ? atoll(s) : 72; return v < 1 ? 1 : v; }();
