@@ -100,8 +100,12 @@ template <int ND, int S> struct RowsCfg {
     static constexpr int ITERS = ROWS * G;
 };
 
-template <int ND, int S, bool W, bool STAG, bool F>
+template <int ND, int S, bool W, bool STAG, bool F, bool KEEP = false>
 __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P, const TileConfig *gate) {
+    // KEEP (the slab passes of a grid larger than L2): mark the accumulator lines evict-last in L2 (red_add_hint,
+    // ptg_stencil.cuh).  A compile-time switch: as a run-time one it cost the L2-resident headline case 6 per cent.
+    constexpr bool keep = KEEP;
+    const unsigned long long keep_pol = KEEP ? l2_keep_policy() : 0ull;
     if (gate != nullptr && gate->mode != kModeRows) return;
     using C = RowsCfg<ND, S>;
     constexpr int NW = C::NW;
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
                 const int l0 = __shfl_sync(0xffffffffu, lin0, p);
                 if (j < NW && l0 >= 0) {
                     const double v = stage[(row * NW + j) * C::KS + p];
-                    red_add(target + (int64_t)l0 + (int64_t)slab * slab_stride + row * row_stride + j, v);
+                    red_add_hint(target + (int64_t)l0 + (int64_t)slab * slab_stride + row * row_stride + j, v, keep, keep_pol);
                 }
             }
             __syncwarp();
@@ -202,8 +206,12 @@ __global__ void __launch_bounds__(kThreads) k_deposit_rows(const DepositParams P
 // which share a pipeline with the reductions (ncu: 54 shared-memory wavefronts per 32 particles next
 // to 96 sector-cycles of REDs).  No warp-level exchange at all, hence no convergence constraints.
 constexpr int kQuadUnroll = 2;
-template <int ND, int S, bool W, bool STAG, bool F>
+template <int ND, int S, bool W, bool STAG, bool F, bool KEEP = false>
 __global__ void __launch_bounds__(kThreads) k_deposit_quads(const DepositParams P, const TileConfig *gate) {
+    // KEEP (the slab passes of a grid larger than L2): mark the accumulator lines evict-last in L2 (red_add_hint,
+    // ptg_stencil.cuh).  A compile-time switch: as a run-time one it cost the L2-resident headline case 6 per cent.
+    constexpr bool keep = KEEP;
+    const unsigned long long keep_pol = KEEP ? l2_keep_policy() : 0ull;
     if (gate != nullptr && gate->mode != kModeRows) return;
     using C = RowsCfg<ND, S>;
     constexpr int NW = C::NW, G = C::G, U = kQuadUnroll;
@@ -256,12 +264,12 @@ __global__ void __launch_bounds__(kThreads) k_deposit_quads(const DepositParams 
 #pragma unroll
             for (int k = 1; k < NW; ++k) wj = j == k ? wl[k] : wj;
             if (ND == 1) {
-                red_add(target + lin, W ? __dmul_rn(wj, w[u]) : wj);
+                red_add_hint(target + lin, W ? __dmul_rn(wj, w[u]) : wj, keep, keep_pol);
             } else if (ND == 2) {
 #pragma unroll
                 for (int a = 0; a < NW; ++a) {
                     const double c = __dmul_rn(wx[a], wj);
-                    red_add(target + lin + a * row_stride, W ? __dmul_rn(c, w[u]) : c);
+                    red_add_hint(target + lin + a * row_stride, W ? __dmul_rn(c, w[u]) : c, keep, keep_pol);
                 }
             } else {
 #pragma unroll
@@ -269,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) k_deposit_quads(const DepositParams 
 #pragma unroll
                     for (int bb = 0; bb < NW; ++bb) {
                         const double c = __dmul_rn(__dmul_rn(wx[a], wy[bb]), wj);
-                        red_add(target + lin + a * slab_stride + bb * row_stride, W ? __dmul_rn(c, w[u]) : c);
+                        red_add_hint(target + lin + a * slab_stride + bb * row_stride, W ? __dmul_rn(c, w[u]) : c, keep, keep_pol);
                     }
             }
         }
@@ -337,6 +345,14 @@ static cudaError_t launch_rows(const DepositParams &P, const TileConfig *gate, i
             k_merge_staggered<<<(int)(mb < cap ? mb : cap), 256, 0, st>>>(P, rows, last, gate);
             return cudaGetLastError();
         }
+    }
+    if (P.slab_lo > -(1 << 30) || P.slab_hi < (1 << 30)) {        // slab pass: the KEEP instances
+        if (quads) {
+            if (W && fused_mode(P)) k_deposit_quads<ND, S, W, false, W, true><<<blocks, kThreads, 0, st>>>(P, gate);
+            else k_deposit_quads<ND, S, W, false, false, true><<<blocks, kThreads, 0, st>>>(P, gate);
+        } else if (W && fused_mode(P)) k_deposit_rows<ND, S, W, false, W, true><<<blocks, kThreads, 0, st>>>(P, gate);
+        else k_deposit_rows<ND, S, W, false, false, true><<<blocks, kThreads, 0, st>>>(P, gate);
+        return cudaGetLastError();
     }
     if (quads) {
         if (W && fused_mode(P)) k_deposit_quads<ND, S, W, false, W><<<blocks, kThreads, 0, st>>>(P, gate);

@@ -329,6 +329,20 @@ __device__ __forceinline__ double particle_weight(const DepositParams &P, int64_
 __device__ __forceinline__ void red_add(double *addr, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
+// The same with the accumulator line marked evict-last in L2 when `keep` is set -- the counterpart of the evict-first
+// particle loads.  Used by the slab passes of grids larger than L2 (ptg_deposit_global.cu): without the hint the
+// particle stream pushes the pass's slab out of L2 (hit rate 47 %, 2.9 GB of accumulator lines written back per pass,
+// profiles/r02/ncu_full_quads_cfg3.txt); with it cfg3 i.i.d. goes from 24.1 to 33.5 Gp/s.  On L2-resident grids the
+// hint buys nothing (cfg2 52.4 vs 51.3 Gp/s, profiles/r02/perf_evictlast.log), hence the switch.
+__device__ __forceinline__ unsigned long long l2_keep_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void red_add_hint(double *addr, double v, bool keep, unsigned long long pol) {
+    if (keep) asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(addr), "d"(v), "l"(pol) : "memory");
+    else asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
 
 // Integer accumulation in global memory, two 64-bit words per cell, in one of two representations:
 //   split (fixed_split = 1, the default): value = hi * 2^31 + lo.  A contribution k is added as its low 31 bits to
